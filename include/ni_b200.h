@@ -1,0 +1,154 @@
+/*
+ * ni_b200.h -- C ABI of the B200-native ODE-ensemble engine (libni_b200.so).
+ *
+ * The reference (Limespy/numba-integrators) has no FFI: its boundary is the Python call
+ * surface `ni.RK45 / ni.RK23 / ni.Advanced / ni.step / ni.ff2t / ni.ff2cond`
+ * (src/numba_integrators/__init__.py:3, _API.py:22-49).  The entry points below are what
+ * that surface binds to when the jitclass solver object (_basic.py:182-271,
+ * _advanced.py:197-278) is replaced by a device-resident ensemble of N trajectories; the
+ * Python facade in numba_integrators_b200/ calls them through ctypes (INTEGRATION.md shows
+ * the stub).  Plain pointers and sizes only -- no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 (NI_OK) or a negative NI_ERR_* code; ni_last_error() gives the
+ *     message of the calling thread's last failure.  No exceptions cross the boundary.
+ *   - host buffers are caller-owned and only read/written during the call (copies go through
+ *     the ensemble's CUDA stream; pass pinned memory for asynchronous copies).
+ *   - device memory is owned by the handle.  One handle = one ensemble on one GPU; calls on
+ *     one handle must be serialised by the caller, different handles are independent.
+ *   - row-major host layouts: y0 / y / klast are N x n, params N x P, aux N x Q.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     NI_ERR_CUDA.
+ */
+#ifndef NI_B200_H
+#define NI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NI_OK 0
+#define NI_ERR_INVALID (-1)     /* bad argument */
+#define NI_ERR_CUDA (-2)        /* CUDA runtime error (no device, launch failure, ...) */
+#define NI_ERR_NVRTC (-3)       /* run-time compilation of a user RHS failed (see ni_module_log) */
+#define NI_ERR_UNSUPPORTED (-4) /* no kernel for this (rhs, n, method) combination */
+#define NI_ERR_NOMEM (-5)
+#define NI_ERR_REC_OVERFLOW (-6) /* record log full: drain it and call run/step again */
+
+/* methods: reference `Solvers.RK23 / Solvers.RK45` (_basic.py:335-339), tableaux _aux.py:77-115 */
+#define NI_RK23 0
+#define NI_RK45 1
+
+/* built-in right-hand sides (p = per-trajectory parameters, aux = auxiliary output) */
+#define NI_RHS_HARMONIC 0    /* y0'=y1, y1'=-y0                    (reference.py:46-49)  */
+#define NI_RHS_LORENZ63 1    /* p=(sigma,rho,beta), aux=x^2+y^2+z^2                      */
+#define NI_RHS_VANDERPOL 2   /* p=(mu)                                                    */
+#define NI_RHS_HEAT1D 3      /* p=(k): dy_j = k (y_{j-1} - 2 y_j + y_{j+1}), Dirichlet 0 */
+#define NI_RHS_BURGERS1D 4   /* p=(nu/dx^2, 1/(2dx))                                      */
+#define NI_RHS_EXPONENTIAL 5 /* y' = y                             (reference.py:54-57)  */
+#define NI_RHS_RICCATI 6     /* y' = 2y/x - x^2 y^2                (reference.py:38-41)  */
+#define NI_RHS_README_ADV 7  /* README.md:80-85, p=(a,b0,b1), aux=a*y1                    */
+#define NI_RHS_BLOWUP 8      /* y' = y^2 (step-too-small exit)                            */
+
+/* per-trajectory status codes (the reference only has step() -> False, _basic.py:135,180) */
+#define NI_ST_RUNNING 0
+#define NI_ST_FINISHED 1  /* a step() call found direction*(t - t_bound) >= 0 */
+#define NI_ST_FAILED 2    /* h_abs fell below 8 ulp(t) (_basic.py:179-180); latched */
+#define NI_ST_NONFINITE 3 /* error norm NaN (the reference would loop forever); latched */
+
+/* fields for ni_ensemble_get / ni_ensemble_set / ni_ensemble_device_ptr.
+ * Names follow the jitclass attributes (_basic.py:182-199). */
+#define NI_F_T 0          /* double[N]                                            */
+#define NI_F_Y 1          /* double[N][n]  (device: [n][N] component-major)       */
+#define NI_F_AUX 2        /* double[N][Q]  `auxiliary` (_advanced.py:276-278)     */
+#define NI_F_H_ABS 3      /* double[N]                                            */
+#define NI_F_STEP_SIZE 4  /* double[N]                                            */
+#define NI_F_KLAST 5      /* double[N][n]  K[-1], the FSAL stage                  */
+#define NI_F_STATUS 6     /* int32[N]                                             */
+#define NI_F_N_ACCEPTED 7 /* int32[N]                                             */
+#define NI_F_N_REJECTED 8 /* int32[N]                                             */
+#define NI_F_RUNNING 9    /* uint8[N]  result of the last step() per trajectory   */
+#define NI_F_T_BOUND 10   /* double[N]  (settable: _API.py:33,37)                 */
+#define NI_F_DIRECTION 11 /* double[N]                                            */
+#define NI_F_PARAMS 12    /* double[N][P]                                         */
+#define NI_F_COND_HIT 13  /* uint8[N]  ff2cond predicate hit                      */
+
+/* predicates for ni_ensemble_ff2cond (checked after every accepted step, _API.py:41-49) */
+#define NI_COND_Y_GT 1
+#define NI_COND_Y_LT 2
+#define NI_COND_AUX_GT 3
+#define NI_COND_AUX_LT 4
+
+typedef struct ni_module ni_module;     /* one compiled (rhs, n, P, Q, method, advanced) kernel set */
+typedef struct ni_ensemble ni_ensemble; /* N trajectories resident on one GPU */
+
+int ni_version(void);
+const char *ni_last_error(void);
+int ni_device_count(int *count);
+
+/* ---- modules -------------------------------------------------------------------------
+ * Replaces numba's JIT specialisation of the solver on the user's RHS
+ * (`nbODEtype`, _aux.py:64-65; `Advanced(parameters_signature, auxiliary_signature, solver)`,
+ * _advanced.py:280-368).  `advanced` selects step_advanced semantics (h = h_abs*direction,
+ * _advanced.py:163) instead of _step's (h = h_abs, _basic.py:148). */
+int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_module **out);
+/* `rhs_body` is the body of
+ *   __device__ void rhs(double t, const double* y, const double* p, double* dy, double* aux)
+ * in CUDA C++; it is fused into the stepper kernels with NVRTC for sm_100a. */
+int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced, const char *nvrtc_options,
+                      ni_module **out);
+int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages);
+const char *ni_module_log(const ni_module *m);
+int ni_module_destroy(ni_module *m);
+
+/* ---- ensembles -----------------------------------------------------------------------
+ * ni_ensemble_create + ni_ensemble_init == the solver constructor RK.__init__
+ * (_basic.py:203-242): FSAL seed K[-1] = f(t0, y0), direction, select_initial_step
+ * (_basic.py:33-89) unless first_step != 0.  t0 / t_bound have N entries when the matching
+ * `*_per_traj` flag is non-zero, else 1.  rtol / atol have n entries (_aux.py:134-140). */
+int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ensemble **out);
+int ni_ensemble_destroy(ni_ensemble *e);
+int ni_ensemble_set_stream(ni_ensemble *e, void *cuda_stream); /* run on the caller's stream */
+int ni_ensemble_upload(ni_ensemble *e, const double *t0, int t0_per_traj, const double *y0, const double *params,
+                       const double *t_bound, int t_bound_per_traj);    /* host -> HBM staging (async) */
+int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *atol, double max_step,
+                      double first_step);                               /* init kernel on resident inputs (async) */
+int ni_ensemble_init(ni_ensemble *e, const double *t0, int t0_per_traj, const double *y0, const double *params,
+                     const double *t_bound, int t_bound_per_traj, const double *rtol, const double *atol,
+                     double max_step, double first_step);               /* upload + reset + sync */
+
+/* ni.step(solver) on every trajectory (_API.py:22-24): at most one accepted step each.
+ * *n_true = number of trajectories whose step() returned True. */
+int ni_ensemble_step(ni_ensemble *e, int64_t *n_true);
+/* `while ni.step(solver): pass` on every trajectory.  *n_unfinished = trajectories still
+ * RUNNING when the call returns (0 unless the record log filled up -> NI_ERR_REC_OVERFLOW). */
+int ni_ensemble_run(ni_ensemble *e, int64_t *n_unfinished);
+int ni_ensemble_run_async(ni_ensemble *e); /* one launch, no host synchronisation */
+int ni_ensemble_sync(ni_ensemble *e);
+/* ni.ff2t (_API.py:27-39).  is_not_last: uint8[N] host buffer or NULL. */
+int ni_ensemble_ff2t(ni_ensemble *e, double t_end, uint8_t *is_not_last);
+/* ni.ff2cond (_API.py:41-49) with a built-in predicate NI_COND_*; hit: uint8[N] or NULL. */
+int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double value, uint8_t *hit, int64_t *n_hit);
+
+int ni_ensemble_get(ni_ensemble *e, int field, void *host_out);
+int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in); /* NI_F_T_BOUND, NI_F_H_ABS */
+int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr);  /* zero-copy view (NCCL gather) */
+int ni_ensemble_set_max_attempts(ni_ensemble *e, int64_t per_launch);
+
+/* ---- recording of accepted steps into an HBM append log --------------------------------
+ * (README.md:62-69 appends solver.t / solver.y after every accepted step.)  Records are
+ * (trajectory, step index, t, y[n], aux[Q]); order within the log is arbitrary. */
+int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity);
+int ni_ensemble_record_count(ni_ensemble *e, int64_t *count);
+int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, double *t, double *y, double *aux,
+                             int64_t max_records, int64_t *n_out);
+
+/* device time of the most recent init / run kernels (CUDA events on the ensemble's stream) */
+int ni_ensemble_timing(ni_ensemble *e, float *ms_init, float *ms_run, int64_t *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NI_B200_H */

@@ -1,0 +1,104 @@
+"""Right-hand sides accepted by the solver constructors.
+
+The reference takes a numba first-class function `float64[:](float64, float64[:])`
+(`_aux.py:64-65`) or, for Advanced, `(float64[:], aux)(float64, float64[:], params)`
+(`_advanced.py:22-26`).  Here the RHS is fused into the CUDA stepper kernels, so it is either a
+built-in (compiled ahead of time for sm_100a) or a CUDA C++ snippet specialised with NVRTC.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+_BUILTIN_IDS = {'harmonic': 0, 'sine': 0, 'lorenz63': 1, 'vanderpol': 2, 'heat1d': 3, 'burgers1d': 4,
+                'exponential': 5, 'riccati': 6, 'readme_advanced': 7, 'blowup': 8}
+# name -> (n or None for "any", P, Q)
+_BUILTIN_SHAPE = {'harmonic': (2, 0, 0), 'sine': (2, 0, 0), 'lorenz63': (3, 3, 1), 'vanderpol': (2, 1, 0),
+                  'heat1d': (None, 1, 0), 'burgers1d': (None, 2, 0), 'exponential': (1, 0, 0), 'riccati': (1, 0, 0),
+                  'readme_advanced': (2, 3, 1), 'blowup': (1, 0, 0)}
+
+
+class RHS:
+    """Base: `n` state dimension (None = taken from y0), `P` parameters, `Q` auxiliary outputs."""
+    name = '?'
+    n = None
+    P = 0
+    Q = 0
+    bound_parameters = None  # parameters closed over (basic API has no `parameters` argument)
+
+    def _module(self, n, method, advanced):
+        raise NotImplementedError
+
+
+class BuiltinRHS(RHS):
+    def __init__(self, name, parameters=None):
+        if name not in _BUILTIN_IDS:
+            raise ValueError(f'unknown built-in right-hand side {name!r}; choose from {sorted(_BUILTIN_IDS)}')
+        self.name = name
+        self.rhs_id = _BUILTIN_IDS[name]
+        self.n, self.P, self.Q = _BUILTIN_SHAPE[name]
+        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
+
+    def __call__(self, *parameters):
+        """Bind parameters (scalars or per-trajectory arrays), e.g. `ni.rhs.vanderpol(mu)`."""
+        if len(parameters) != self.P:
+            raise ValueError(f'{self.name} takes {self.P} parameters, got {len(parameters)}')
+        cols = np.broadcast_arrays(*[np.asarray(p, dtype=np.float64) for p in parameters]) if parameters else []
+        par = np.stack(cols, axis=-1) if cols else None
+        return BuiltinRHS(self.name, par)
+
+    def _module(self, n, method, advanced):
+        out = _lib._vp()
+        _lib.check(_lib.lib().ni_module_builtin(self.rhs_id, int(n), int(method), int(bool(advanced)), out))
+        return out
+
+    def __repr__(self):
+        return f'BuiltinRHS({self.name!r})'
+
+
+class CudaRHS(RHS):
+    """User right-hand side: the body of
+
+        __device__ void rhs(double t, const double* y, const double* p, double* dy, double* aux)
+
+    in CUDA C++.  It is fused into the RK stage loop at load time with NVRTC (sm_100a).
+    """
+
+    def __init__(self, body, n, P=0, Q=0, parameters=None, name='user', nvrtc_options=''):
+        self.body, self.n, self.P, self.Q, self.name = str(body), int(n), int(P), int(Q), name
+        self.nvrtc_options = nvrtc_options
+        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
+
+    def _module(self, n, method, advanced):
+        if n != self.n:
+            raise ValueError(f'y0 has {n} components, the RHS was declared with n={self.n}')
+        out = _lib._vp()
+        _lib.check(_lib.lib().ni_module_compile(self.body.encode(), self.n, self.P, self.Q, int(method),
+                                                int(bool(advanced)), self.nvrtc_options.encode(), out))
+        return out
+
+    def __repr__(self):
+        return f'CudaRHS({self.name!r}, n={self.n}, P={self.P}, Q={self.Q})'
+
+
+harmonic = BuiltinRHS('harmonic')
+sine = harmonic
+lorenz63 = BuiltinRHS('lorenz63')
+vanderpol = BuiltinRHS('vanderpol')
+heat1d = BuiltinRHS('heat1d')
+burgers1d = BuiltinRHS('burgers1d')
+exponential = BuiltinRHS('exponential')
+riccati = BuiltinRHS('riccati')
+readme_advanced = BuiltinRHS('readme_advanced')
+blowup = BuiltinRHS('blowup')
+
+
+def as_rhs(f) -> RHS:
+    if isinstance(f, RHS):
+        return f
+    if isinstance(f, str):
+        return BuiltinRHS(f)
+    raise TypeError('the right-hand side must be a built-in name / ni.rhs.* object or a ni.CudaRHS snippet; '
+                    'Python / numba callables cannot be fused into the CUDA kernels '
+                    f'(got {type(f).__name__})')

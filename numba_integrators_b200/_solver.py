@@ -1,0 +1,407 @@
+"""Solver objects and factories: the reference's L2/L3 layers on top of the C ABI.
+
+Mirrors (file:line under /root/reference/src/numba_integrators/):
+  RK jitclass + attributes          _basic.py:182-271      -> Ensemble
+  RK23 / RK45 factories, defaults   _basic.py:273-333      -> RK23 / RK45
+  ALL, Solvers                      _basic.py:335-339      -> ALL, Solvers
+  Advanced factory                  _advanced.py:280-368   -> Advanced
+  convert / _into_1d_typearray      _aux.py:117-140        -> convert
+  step / ff2t / ff2cond             _API.py:22-49          -> step / ff2t / ff2cond
+`y0` of shape (n,) gives a single solver whose attributes are scalars / (n,) arrays exactly as
+in the reference; `y0` of shape (N, n) gives an N-trajectory ensemble (attributes gain a
+leading N axis, `step()` returns a mask whose truth value is `any()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from collections.abc import Iterable
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from ._rhs import RHS, as_rhs
+
+SAFETY = 0.9       # _aux.py:16
+MIN_FACTOR = 0.2   # _aux.py:18
+MAX_FACTOR = 10    # _aux.py:19
+
+# Tableaux (_aux.py:77-115); the kernels carry the same constants (csrc/ni_core.cuh NiTab<>)
+RK23_A = np.array(((0, 0, 0), (1 / 2, 0, 0), (0, 3 / 4, 0)), dtype=np.float64)
+RK23_B = np.array((2 / 9, 1 / 3, 4 / 9), dtype=np.float64)
+RK23_C = np.array((0, 1 / 2, 3 / 4), dtype=np.float64)
+RK23_E = np.array((5 / 72, -1 / 12, -1 / 9, 1 / 8), dtype=np.float64)
+RK45_A = np.array(((0., 0., 0., 0., 0.),
+                   (1 / 5, 0., 0., 0., 0.),
+                   (3 / 40, 9 / 40, 0., 0., 0.),
+                   (44 / 45, -56 / 15, 32 / 9, 0., 0.),
+                   (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729, 0),
+                   (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656)), dtype=np.float64)
+RK45_B = np.array((35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84), dtype=np.float64)
+RK45_C = np.array((0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1), dtype=np.float64)
+RK45_E = np.array((-71 / 57600, 0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40), dtype=np.float64)
+_TABLEAU = {_lib.RK23: (2, 3, RK23_A, RK23_B, RK23_C, RK23_E), _lib.RK45: (4, 6, RK45_A, RK45_B, RK45_C, RK45_E)}
+
+
+def _into_1d_typearray(item, length=1, dtype=np.float64, max_ndim=1):
+    """_aux.py:117-132, extended: y0 may also be (N, n)."""
+    if isinstance(item, np.ndarray):
+        if item.ndim == 0:
+            return np.full(length, item, dtype=dtype)
+        elif item.ndim <= max_ndim:
+            return np.ascontiguousarray(item, dtype=dtype)
+        else:
+            raise ValueError(f'Dimensionality of y0 is over {max_ndim}. y0 = {item}')
+    elif isinstance(item, Iterable):
+        return _into_1d_typearray(np.array(item, dtype=dtype), length, dtype, max_ndim)
+    else:
+        return np.full(length, item, dtype=dtype)
+
+
+def convert(y0, rtol, atol):
+    """Converts y0 and tolerances into float64 arrays; tolerances broadcast to len(y0) (_aux.py:134-140)."""
+    y0 = _into_1d_typearray(y0, max_ndim=2)
+    n = y0.shape[-1]
+    return y0, _into_1d_typearray(rtol, n), _into_1d_typearray(atol, n)
+
+
+class StepMask(np.ndarray):
+    """Per-trajectory bool result of step()/ff2t() on an ensemble; truthy while ANY trajectory is."""
+
+    def __bool__(self):
+        return bool(self.any())
+
+
+def _mask(a):
+    return np.asarray(a, dtype=bool).view(StepMask)
+
+
+class Records:
+    """Accepted steps drained from the HBM record log."""
+
+    def __init__(self, traj, step, t, y, aux):
+        self.traj, self.step, self.t, self.y, self.aux = traj, step, t, y, aux
+
+    def __len__(self):
+        return len(self.t)
+
+    def sorted(self):
+        """Records ordered by (trajectory, step index)."""
+        o = np.lexsort((self.step, self.traj))
+        return Records(self.traj[o], self.step[o], self.t[o], self.y[o], self.aux[o])
+
+    def trajectory(self, i):
+        r = self.sorted()
+        m = r.traj == i
+        return r.t[m], r.y[m], r.aux[m]
+
+
+class Ensemble:
+    """Device-resident solver state: N trajectories of one ODE on one GPU.
+
+    Attribute names follow the reference's jitclass spec (`_basic.py:182-199`).
+    """
+
+    def __init__(self, fun, t0, y0, t_bound, max_step, rtol, atol, first_step, method, advanced=False,
+                 parameters=None, device=None, record=0, allow_reference_backward_bug=False):
+        self._h = None
+        self._mod = None
+        self._L = _lib.lib()
+        self.fun = as_rhs(fun)
+        y0, rtol, atol = convert(y0, rtol, atol)
+        self._single = y0.ndim == 1
+        y0 = np.atleast_2d(y0)
+        self.N, self.n = y0.shape
+        if self.fun.n is not None and self.fun.n != self.n:
+            raise ValueError(f'{self.fun!r} has {self.fun.n} components, y0 has {self.n}')
+        if len(rtol) != self.n or len(atol) != self.n:
+            raise ValueError('rtol / atol must be scalars or have one entry per component')
+        self._method = method
+        self._advanced = bool(advanced)
+        order, self.n_stages, self.A, self.B, self.C, self.E = _TABLEAU[method]
+        self.error_exponent = -1 / (order + 1)
+        self.rtol, self.atol = rtol, atol
+        self.max_step = float(max_step)
+        self._first_step = float(first_step)
+        t0a = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (self.N,)))
+        tba = np.ascontiguousarray(np.broadcast_to(np.asarray(t_bound, dtype=np.float64), (self.N,)))
+        if not self._advanced and not allow_reference_backward_bug and np.any(tba < t0a):
+            raise ValueError('the basic RK23/RK45 ignore `direction` when forming the step (_basic.py:148) and '
+                             'never reach a t_bound < t0; build the solver through ni.Advanced for backward runs')
+        if parameters is None:
+            parameters = self.fun.bound_parameters
+        P = self.fun.P
+        if P:
+            if parameters is None:
+                raise ValueError(f'{self.fun!r} needs {P} parameters per trajectory')
+            par = _flatten_parameters(parameters)
+            if par.ndim == 1:
+                par = par.reshape(1, -1)
+            if par.shape[-1] != P:
+                raise ValueError(f'{self.fun!r} takes {P} parameters, got {par.shape[-1]}')
+            par = np.ascontiguousarray(np.broadcast_to(par, (self.N, P)))
+        else:
+            par = None
+        self.P, self.Q = P, self.fun.Q
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+        self.device = int(device)
+
+        self._mod = self.fun._module(self.n, method, self._advanced)
+        h = _lib._vp()
+        check(self._L.ni_ensemble_create(self._mod, self.device, self.N, h))
+        self._h = h
+        if record:
+            self.record_enable(record)
+        check(self._L.ni_ensemble_init(self._h, t0a.ctypes.data, 1, y0.ctypes.data,
+                                       par.ctypes.data if par is not None else None, tba.ctypes.data, 1,
+                                       rtol.ctypes.data_as(_lib._dp), atol.ctypes.data_as(_lib._dp), self.max_step,
+                                       self._first_step))
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.ni_ensemble_destroy(self._h)
+            self._h = None
+        if getattr(self, '_mod', None):
+            self._L.ni_module_destroy(self._mod)
+            self._mod = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ field access
+    def _get(self, field, comps, dtype=np.float64):
+        shape = (self.N,) if comps is None else (self.N, comps)
+        out = np.empty(shape, dtype=dtype)
+        if out.size:
+            check(self._L.ni_ensemble_get(self._h, field, out.ctypes.data))
+        return out
+
+    def _scalar_or_array(self, a):
+        if self._single:
+            return a[0].item() if a.ndim == 1 else a[0]
+        return a
+
+    t = property(lambda s: s._scalar_or_array(s._get(_lib.F_T, None)))
+    y = property(lambda s: s._scalar_or_array(s._get(_lib.F_Y, s.n)))
+    auxiliary = property(lambda s: s._scalar_or_array(s._get(_lib.F_AUX, s.Q)))
+    step_size = property(lambda s: s._scalar_or_array(s._get(_lib.F_STEP_SIZE, None)))
+    direction = property(lambda s: s._scalar_or_array(s._get(_lib.F_DIRECTION, None)))
+    parameters = property(lambda s: s._scalar_or_array(s._get(_lib.F_PARAMS, s.P)))
+    status = property(lambda s: s._scalar_or_array(s._get(_lib.F_STATUS, None, np.int32)))
+    n_accepted = property(lambda s: s._scalar_or_array(s._get(_lib.F_N_ACCEPTED, None, np.int32)))
+    n_rejected = property(lambda s: s._scalar_or_array(s._get(_lib.F_N_REJECTED, None, np.int32)))
+
+    @property
+    def nfev(self):
+        """RHS evaluations: 1 (FSAL seed) + 1 (select_initial_step) + n_stages per attempt."""
+        n_init = 2 if self._first_step == 0.0 else 1
+        return n_init + self.n_stages * (self.n_accepted + self.n_rejected)
+
+    def _set(self, field, value):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (self.N,)))
+        check(self._L.ni_ensemble_set(self._h, field, a.ctypes.data))
+
+    @property
+    def t_bound(self):
+        return self._scalar_or_array(self._get(_lib.F_T_BOUND, None))
+
+    @t_bound.setter
+    def t_bound(self, value):  # the one field the reference API itself writes (_API.py:33,37)
+        self._set(_lib.F_T_BOUND, value)
+
+    @property
+    def h_abs(self):
+        return self._scalar_or_array(self._get(_lib.F_H_ABS, None))
+
+    @h_abs.setter
+    def h_abs(self, value):
+        self._set(_lib.F_H_ABS, value)
+
+    @property
+    def K(self):
+        """Stage matrix (n_stages+1, n).  Only K[-1] (the FSAL stage, the one that carries state
+        between steps) is kept on the device; rows 0..n_stages-1 are scratch in the reference
+        (overwritten by every attempt) and read NaN here."""
+        kl = self._get(_lib.F_KLAST, self.n)
+        K = np.full((self.N, self.n_stages + 1, self.n), np.nan)
+        K[:, -1, :] = kl
+        return K[0] if self._single else K
+
+    @property
+    def state(self):  # _basic.py:269-271 / _advanced.py:276-278
+        return (self.t, self.y, self.auxiliary) if self._advanced else (self.t, self.y)
+
+    # ------------------------------------------------------------------ stepping
+    def step(self):
+        """One `solver.step()` on every trajectory (_basic.py:244-267)."""
+        n_true = C.c_int64(0)
+        check(self._L.ni_ensemble_step(self._h, n_true))
+        if self._single:
+            return bool(n_true.value)
+        return _mask(self._get(_lib.F_RUNNING, None, np.uint8))
+
+    def run(self):
+        """`while step(): pass` for every trajectory, on the device.  Returns #trajectories not finished."""
+        left = C.c_int64(0)
+        check(self._L.ni_ensemble_run(self._h, left))
+        return left.value
+
+    def ff2t(self, t_end):
+        flags = np.zeros(self.N, dtype=np.uint8)
+        check(self._L.ni_ensemble_ff2t(self._h, float(t_end), flags.ctypes.data))
+        return bool(flags[0]) if self._single else _mask(flags)
+
+    def ff2cond_device(self, kind, index, value):
+        hit = np.zeros(self.N, dtype=np.uint8)
+        n_hit = C.c_int64(0)
+        check(self._L.ni_ensemble_ff2cond(self._h, int(kind), int(index), float(value), hit.ctypes.data, n_hit))
+        return bool(hit[0]) if self._single else _mask(hit)
+
+    # ------------------------------------------------------------------ recording
+    def record_enable(self, capacity):
+        check(self._L.ni_ensemble_record_enable(self._h, int(capacity)))
+        self._rec_cap = int(capacity)
+
+    def record_count(self):
+        c = C.c_int64(0)
+        check(self._L.ni_ensemble_record_count(self._h, c))
+        return c.value
+
+    def record_drain(self) -> Records:
+        c = self.record_count()
+        traj, step = np.empty(c, np.uint32), np.empty(c, np.uint32)
+        t, y, aux = np.empty(c), np.empty((c, self.n)), np.empty((c, self.Q))
+        n_out = C.c_int64(0)
+        check(self._L.ni_ensemble_record_drain(self._h, traj.ctypes.data, step.ctypes.data, t.ctypes.data,
+                                               y.ctypes.data, aux.ctypes.data if self.Q else None, c, n_out))
+        k = n_out.value
+        return Records(traj[:k], step[:k], t[:k], y[:k], aux[:k])
+
+    # ------------------------------------------------------------------ misc
+    def device_pointer(self, field):
+        p = _lib._vp()
+        check(self._L.ni_ensemble_device_ptr(self._h, field, p))
+        return p.value
+
+    def timing(self):
+        a, b, c = C.c_float(0), C.c_float(0), C.c_int64(0)
+        check(self._L.ni_ensemble_timing(self._h, a, b, c))
+        return dict(ms_init=a.value, ms_run=b.value, launches=c.value)
+
+
+def _flatten_parameters(parameters):
+    """Reference parameters can be any numba-typed value (README.md:88 uses `(2., array((-1., 1.)))`);
+    here they are a flat float64 vector per trajectory."""
+    if isinstance(parameters, np.ndarray):
+        return parameters.astype(np.float64, copy=False)
+    if isinstance(parameters, (tuple, list)) and any(isinstance(p, (np.ndarray, list, tuple)) for p in parameters):
+        return np.concatenate([np.ravel(np.asarray(p, dtype=np.float64)) for p in parameters])
+    return np.atleast_1d(np.asarray(parameters, dtype=np.float64))
+
+
+# Type aliases of the reference API (`_basic.py:183`, `_aux.py:34`)
+RK = Ensemble
+Solver = Ensemble
+
+
+# ---------------------------------------------------------------------- factories
+def RK23(fun, t0, y0, t_bound, max_step=np.inf, rtol=1e-3, atol=1e-6, first_step=0, **kw):  # _basic.py:291-302
+    return Ensemble(fun, t0, y0, t_bound, max_step, rtol, atol, first_step, _lib.RK23, **kw)
+
+
+def RK45(fun, t0, y0, t_bound, max_step=np.inf, rtol=1e-3, atol=1e-6, first_step=0., **kw):  # _basic.py:323-333
+    return Ensemble(fun, t0, y0, t_bound, max_step, rtol, atol, first_step, _lib.RK45, **kw)
+
+
+ALL = (RK23, RK45)
+
+
+class Solvers(enum.Enum):  # _basic.py:336-339: RK23/RK45 are plain functions, only ALL is a member
+    RK23 = RK23
+    RK45 = RK45
+    ALL = ALL
+
+
+def Advanced(parameters_signature, auxiliary_signature, solver):
+    """Factory of solvers whose RHS takes per-trajectory `parameters` and returns an `auxiliary`
+    output (_advanced.py:280-368).  The numba type signatures of the reference become optional
+    length checks: pass ints (P, Q) or anything else (ignored; the RHS object knows P and Q)."""
+
+    def _check(fun):
+        f = as_rhs(fun)
+        if isinstance(parameters_signature, int) and parameters_signature != f.P:
+            raise ValueError(f'parameters_signature says {parameters_signature} parameters, {f!r} takes {f.P}')
+        if isinstance(auxiliary_signature, int) and auxiliary_signature != f.Q:
+            raise ValueError(f'auxiliary_signature says {auxiliary_signature} outputs, {f!r} returns {f.Q}')
+        return f
+
+    def RK23_advanced(fun, t0, y0, parameters, t_bound, max_step=np.inf, rtol=1e-3, atol=1e-6, first_step=0., **kw):
+        return Ensemble(_check(fun), t0, y0, t_bound, max_step, rtol, atol, first_step, _lib.RK23, advanced=True,
+                        parameters=parameters, **kw)
+
+    def RK45_advanced(fun, t0, y0, parameters, t_bound, max_step=np.inf, rtol=1e-3, atol=1e-6, first_step=0., **kw):
+        return Ensemble(_check(fun), t0, y0, t_bound, max_step, rtol, atol, first_step, _lib.RK45, advanced=True,
+                        parameters=parameters, **kw)
+
+    if solver is RK23:
+        return RK23_advanced
+    if solver is RK45:
+        return RK45_advanced
+    if solver in (Solvers.ALL, ALL):
+        return {Solvers.RK23: RK23_advanced, Solvers.RK45: RK45_advanced}
+    raise ValueError('solver must be ni.RK23, ni.RK45 or ni.Solvers.ALL')
+
+
+# ---------------------------------------------------------------------- drivers (_API.py:22-49)
+def step(solver) -> bool:
+    return solver.step()
+
+
+def ff2t(solver, t_end):
+    """Fast forwards to given time or t_bound."""
+    return solver.ff2t(t_end)
+
+
+class Condition:
+    """Device-side predicate for ff2cond: `kind` compares y[index] / auxiliary[index] with the
+    `parameters` value handed to ff2cond."""
+
+    def __init__(self, kind, index):
+        self.kind, self.index = kind, index
+
+
+def y_above(index=0):
+    return Condition(_lib.COND_Y_GT, index)
+
+
+def y_below(index=0):
+    return Condition(_lib.COND_Y_LT, index)
+
+
+def aux_above(index=0):
+    return Condition(_lib.COND_AUX_GT, index)
+
+
+def aux_below(index=0):
+    return Condition(_lib.COND_AUX_LT, index)
+
+
+def ff2cond(solver, condition, parameters):
+    """Fast forwards until `condition(solver, parameters)` holds after an accepted step.
+
+    `condition` is either a device predicate (ni.y_above(i), ...) evaluated inside the kernel, or
+    any Python callable `(solver, parameters) -> bool`, evaluated on the host after every
+    lock-step `step()` exactly like _API.py:45-49."""
+    if isinstance(condition, Condition):
+        return solver.ff2cond_device(condition.kind, condition.index, parameters)
+    while solver.step():
+        if condition(solver, parameters):
+            return True
+    return False

@@ -1,0 +1,812 @@
+// ni_b200.cu -- C-ABI implementation (include/ni_b200.h) of the B200 ODE-ensemble engine.
+//
+// Host side only: handle management, HBM allocation, host<->device copies, kernel launches,
+// NVRTC specialisation of user right-hand sides.  All arithmetic of the hot path lives in the
+// kernels of ni_core.cuh / ni_large.cuh.  There is no CPU fallback: every compute entry point
+// fails with NI_ERR_CUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ni_b200.h"
+#include "ni_host.h"
+#include "ni_large_host.h"
+#include "ni_rhs_builtin.cuh"
+
+#define NI_API extern "C" __attribute__((visibility("default")))
+
+extern const char ni_core_source[];   // ni_core.cuh as a string (generated: ni_core_src.cpp)
+extern const char ni_large_source[];  // ni_large.cuh as a string
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(NI_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+NI_API int ni_version(void) { return 100; }
+NI_API const char *ni_last_error(void) { return g_err.c_str(); }
+NI_API int ni_device_count(int *count) {
+  if (!count) return fail(NI_ERR_INVALID, "count is NULL");
+  *count = 0;
+  CU(cudaGetDeviceCount(count));
+  return NI_OK;
+}
+
+// ------------------------------------------------------------------ modules
+struct ni_module {
+  int kind = NI_KIND_SMALL;
+  int n = 0, P = 0, Q = 0, method = NI_RK45, advanced = 0, S = 6;
+  const void *k_init = nullptr;
+  const void *k_run[2] = {nullptr, nullptr};  // [record]
+  int block = NI_BLOCK;
+  size_t smem = 0;
+  NiLargePlan large{};       // kernel-class specific launch plan (CTA-per-trajectory)
+  cudaLibrary_t lib = nullptr;  // NVRTC modules only
+  std::string log;
+};
+
+static const NiKernelSet *builtin_small(int rhs_id, int n) {
+  switch (rhs_id) {
+    case NI_RHS_HARMONIC: return n == 2 ? ni_kset_harmonic() : nullptr;
+    case NI_RHS_LORENZ63: return n == 3 ? ni_kset_lorenz63() : nullptr;
+    case NI_RHS_VANDERPOL: return n == 2 ? ni_kset_vanderpol() : nullptr;
+    case NI_RHS_EXPONENTIAL: return n == 1 ? ni_kset_exponential1() : nullptr;
+    case NI_RHS_RICCATI: return n == 1 ? ni_kset_riccati() : nullptr;
+    case NI_RHS_README_ADV: return n == 2 ? ni_kset_readme_adv() : nullptr;
+    case NI_RHS_BLOWUP: return n == 1 ? ni_kset_blowup() : nullptr;
+    default: return nullptr;
+  }
+}
+
+NI_API int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_module **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
+  if (n < 1) return fail(NI_ERR_INVALID, "n must be >= 1");
+  advanced = advanced ? 1 : 0;
+  ni_module *m = new ni_module;
+  m->method = method;
+  m->advanced = advanced;
+  m->S = method == NI_RK45 ? 6 : 3;
+  if (const NiKernelSet *ks = builtin_small(rhs_id, n)) {
+    m->kind = NI_KIND_SMALL;
+    m->n = ks->n;
+    m->P = ks->P;
+    m->Q = ks->Q;
+    m->k_init = ks->init[method];
+    m->k_run[0] = ks->run[method][advanced][0];
+    m->k_run[1] = ks->run[method][advanced][1];
+    *out = m;
+    return NI_OK;
+  }
+  if (ni_large_builtin(rhs_id, n, method, advanced, &m->large, &m->P, &m->Q)) {
+    m->kind = NI_KIND_LARGE;
+    m->n = n;
+    m->k_init = m->large.k_init;
+    m->k_run[0] = m->large.k_run[0];
+    m->k_run[1] = m->large.k_run[1];
+    m->block = m->large.threads;
+    m->smem = m->large.smem_bytes;
+    *out = m;
+    return NI_OK;
+  }
+  delete m;
+  return fail(NI_ERR_UNSUPPORTED, "no built-in kernel for rhs_id=%d with n=%d", rhs_id, n);
+}
+
+// ---- NVRTC (loaded lazily so that the library also loads on machines without it)
+typedef struct _nvrtcProgram *nvrtcProgram;
+struct NvrtcApi {
+  void *h = nullptr;
+  int (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+  int (*DestroyProgram)(nvrtcProgram *);
+  int (*CompileProgram)(nvrtcProgram, int, const char *const *);
+  int (*GetProgramLogSize)(nvrtcProgram, size_t *);
+  int (*GetProgramLog)(nvrtcProgram, char *);
+  int (*GetCUBINSize)(nvrtcProgram, size_t *);
+  int (*GetCUBIN)(nvrtcProgram, char *);
+  const char *(*GetErrorString)(int);
+};
+static NvrtcApi g_nvrtc;
+static std::mutex g_nvrtc_mu;
+
+static int load_nvrtc() {
+  std::lock_guard<std::mutex> lk(g_nvrtc_mu);
+  if (g_nvrtc.h) return NI_OK;
+  const char *names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                         "/usr/local/cuda/lib64/libnvrtc.so"};
+  void *h = nullptr;
+  if (const char *env = getenv("NI_B200_NVRTC")) h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+  for (size_t i = 0; !h && i < sizeof(names) / sizeof(names[0]); ++i) h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(NI_ERR_NVRTC, "cannot load libnvrtc (%s); set NI_B200_NVRTC to its path", dlerror());
+#define NI_SYM(field, name)                                                       \
+  *(void **)(&g_nvrtc.field) = dlsym(h, name);                                    \
+  if (!g_nvrtc.field) {                                                           \
+    dlclose(h);                                                                   \
+    return fail(NI_ERR_NVRTC, "libnvrtc lacks %s", name);                         \
+  }
+  NI_SYM(CreateProgram, "nvrtcCreateProgram")
+  NI_SYM(DestroyProgram, "nvrtcDestroyProgram")
+  NI_SYM(CompileProgram, "nvrtcCompileProgram")
+  NI_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+  NI_SYM(GetProgramLog, "nvrtcGetProgramLog")
+  NI_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+  NI_SYM(GetCUBIN, "nvrtcGetCUBIN")
+  NI_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef NI_SYM
+  g_nvrtc.h = h;
+  return NI_OK;
+}
+
+NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced,
+                             const char *nvrtc_options, ni_module **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!rhs_body) return fail(NI_ERR_INVALID, "rhs_body is NULL");
+  if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
+  if (n < 1 || P < 0 || Q < 0) return fail(NI_ERR_INVALID, "need n >= 1, P >= 0, Q >= 0");
+  if (n > NI_MAX_SMALL_N)
+    return fail(NI_ERR_UNSUPPORTED, "user RHS snippets support n <= %d (got %d); larger systems use the built-in "
+                "method-of-lines kernels", NI_MAX_SMALL_N, n);
+  if (int rc = load_nvrtc()) return rc;
+  advanced = advanced ? 1 : 0;
+
+  std::string src;
+  src += "#include \"ni_core.cuh\"\n";
+  src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
+         ", Q = " + std::to_string(Q) + ";\n";
+  src += "  NI_DEV static void eval(double t, const double* y, const double* p, double* dy, double* aux) {\n";
+  src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
+  src += rhs_body;
+  src += "\n  }\n};\n";
+  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false";
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
+         "ni_small_init_body<NiUserRhs, " + M + ">(a); }\n";
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_run(const NiArgs a) { "
+         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false>(a); }\n";
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_run_rec(const NiArgs a) { "
+         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true>(a); }\n";
+
+  nvrtcProgram prog = nullptr;
+  const char *hdr_src[] = {ni_core_source};
+  const char *hdr_name[] = {"ni_core.cuh"};
+  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 1, hdr_src, hdr_name);
+  if (rc) return fail(NI_ERR_NVRTC, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(rc));
+  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
+                                   "-default-device"};
+  if (nvrtc_options && *nvrtc_options) {  // space separated extra options
+    std::string o(nvrtc_options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(' ', pos);
+      if (e == std::string::npos) e = o.size();
+      if (e > pos) opts.push_back(o.substr(pos, e - pos));
+      pos = e + 1;
+    }
+  }
+  std::vector<const char *> copts;
+  for (auto &s : opts) copts.push_back(s.c_str());
+  rc = g_nvrtc.CompileProgram(prog, (int)copts.size(), copts.data());
+  ni_module *m = new ni_module;
+  size_t lsz = 0;
+  if (g_nvrtc.GetProgramLogSize(prog, &lsz) == 0 && lsz > 1) {
+    m->log.resize(lsz);
+    g_nvrtc.GetProgramLog(prog, &m->log[0]);
+  }
+  if (rc) {
+    int code = fail(NI_ERR_NVRTC, "nvrtcCompileProgram: %s\n%s", g_nvrtc.GetErrorString(rc), m->log.c_str());
+    g_nvrtc.DestroyProgram(&prog);
+    delete m;
+    return code;
+  }
+  size_t csz = 0;
+  g_nvrtc.GetCUBINSize(prog, &csz);
+  std::vector<char> cubin(csz);
+  g_nvrtc.GetCUBIN(prog, cubin.data());
+  g_nvrtc.DestroyProgram(&prog);
+
+  cudaError_t ce = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  cudaKernel_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
+  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&k0, m->lib, "ni_user_init");
+  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&k1, m->lib, "ni_user_run");
+  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&k2, m->lib, "ni_user_run_rec");
+  if (ce != cudaSuccess) {
+    int code = fail(NI_ERR_CUDA, "loading the compiled RHS module: %s", cudaGetErrorString(ce));
+    if (m->lib) cudaLibraryUnload(m->lib);
+    delete m;
+    return code;
+  }
+  m->kind = NI_KIND_SMALL;
+  m->n = n;
+  m->P = P;
+  m->Q = Q;
+  m->method = method;
+  m->advanced = advanced;
+  m->S = method == NI_RK45 ? 6 : 3;
+  m->k_init = (const void *)k0;
+  m->k_run[0] = (const void *)k1;
+  m->k_run[1] = (const void *)k2;
+  *out = m;
+  return NI_OK;
+}
+
+NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages) {
+  if (!m) return fail(NI_ERR_INVALID, "module is NULL");
+  if (n) *n = m->n;
+  if (P) *P = m->P;
+  if (Q) *Q = m->Q;
+  if (method) *method = m->method;
+  if (advanced) *advanced = m->advanced;
+  if (n_stages) *n_stages = m->S;
+  return NI_OK;
+}
+NI_API const char *ni_module_log(const ni_module *m) { return m ? m->log.c_str() : ""; }
+NI_API int ni_module_destroy(ni_module *m) {
+  if (!m) return NI_OK;
+  if (m->lib) cudaLibraryUnload(m->lib);
+  delete m;
+  return NI_OK;
+}
+
+// ------------------------------------------------------------------ ensembles
+struct ni_ensemble {
+  ni_module mod;  // copy of the module description (kernels stay valid while the module lives)
+  int device = 0;
+  int64_t N = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sms = 148, blocks_per_sm = 1;
+  NiArgs a{};
+  // owned device allocations
+  std::vector<void *> allocs;
+  double *y0_rows = nullptr, *t0_d = nullptr, *tb0_d = nullptr, *params_rows = nullptr;
+  double *tb_saved = nullptr;
+  unsigned char *flag_d = nullptr;
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  bool uploaded = false, initialised = false;
+  int64_t max_attempts = 1ll << 40;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t n_launches = 0;
+  bool have_init_t = false, have_run_t = false;
+};
+
+template <class T>
+static int dalloc(ni_ensemble *e, T **p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  void *q = nullptr;
+  cudaError_t ce = cudaMalloc(&q, count * sizeof(T));
+  if (ce != cudaSuccess) return fail(ce == cudaErrorMemoryAllocation ? NI_ERR_NOMEM : NI_ERR_CUDA, "cudaMalloc(%zu bytes): %s",
+                                     count * sizeof(T), cudaGetErrorString(ce));
+  e->allocs.push_back(q);
+  *p = (T *)q;
+  return NI_OK;
+}
+
+static int need_scratch(ni_ensemble *e, size_t bytes) {
+  if (bytes <= e->scratch_bytes) return NI_OK;
+  void *q = nullptr;
+  cudaError_t ce = cudaMalloc(&q, bytes);
+  if (ce != cudaSuccess) return fail(NI_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(ce));
+  if (e->scratch) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->scratch);
+  }
+  e->scratch = q;
+  e->scratch_bytes = bytes;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_destroy(ni_ensemble *e) {
+  if (!e) return NI_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void *p : e->allocs) cudaFree(p);
+  if (e->scratch) cudaFree(e->scratch);
+  for (auto &ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ensemble **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!m) return fail(NI_ERR_INVALID, "module is NULL");
+  if (N < 1) return fail(NI_ERR_INVALID, "N must be >= 1");
+  if (N > 0xffffffffll) return fail(NI_ERR_INVALID, "N must fit 32 bits per GPU");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(NI_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  ni_ensemble *e = new ni_ensemble;
+  e->mod = *m;
+  e->mod.lib = nullptr;  // not owned
+  e->device = device;
+  e->N = N;
+  const int n = m->n, P = m->P, Q = m->Q;
+  int rc = NI_OK;
+  cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) {
+    delete e;
+    return fail(NI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce));
+  }
+  e->own_stream = true;
+  for (auto &ev : e->ev) cudaEventCreate(&ev);
+  cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+  NiArgs &a = e->a;
+  a.N = N;
+  const size_t sN = (size_t)N;
+#define NI_TRY(x)                \
+  if (rc == NI_OK) rc = (x);
+  NI_TRY(dalloc(e, &a.t, sN))
+  NI_TRY(dalloc(e, &a.h_abs, sN))
+  NI_TRY(dalloc(e, &a.step_size, sN))
+  NI_TRY(dalloc(e, &a.y, sN * n))
+  NI_TRY(dalloc(e, &a.klast, sN * n))
+  NI_TRY(dalloc(e, &a.aux, sN * Q))
+  NI_TRY(dalloc(e, &a.params, sN * P))
+  NI_TRY(dalloc(e, &a.t_bound, sN))
+  NI_TRY(dalloc(e, &a.direction, sN))
+  NI_TRY(dalloc(e, &a.status, sN))
+  NI_TRY(dalloc(e, &a.n_acc, sN))
+  NI_TRY(dalloc(e, &a.n_rej, sN))
+  NI_TRY(dalloc(e, &a.running, sN))
+  NI_TRY(dalloc(e, &a.cond_hit, sN))
+  NI_TRY(dalloc(e, &a.queue, 8))
+  NI_TRY(dalloc(e, &a.rec_cursor, 1))
+  NI_TRY(dalloc(e, &e->y0_rows, sN * n))
+  NI_TRY(dalloc(e, &e->t0_d, sN))
+  NI_TRY(dalloc(e, &e->tb0_d, sN))
+  NI_TRY(dalloc(e, &e->params_rows, sN * P))
+  NI_TRY(dalloc(e, &e->tb_saved, sN))
+  NI_TRY(dalloc(e, &e->flag_d, sN))
+  if (rc == NI_OK && m->kind == NI_KIND_LARGE) rc = ni_large_prepare(&e->mod.large, &a, n, device, e->sms) ? NI_OK : fail(NI_ERR_CUDA, "large-kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+#undef NI_TRY
+  if (rc != NI_OK) {
+    std::string keep = g_err;
+    ni_ensemble_destroy(e);
+    g_err = keep;
+    return rc;
+  }
+  cudaMemsetAsync(a.rec_cursor, 0, sizeof(unsigned long long), e->stream);
+  cudaMemsetAsync(a.cond_hit, 0, sN, e->stream);
+  a.rec_cap = 0;
+  a.max_step = __builtin_inf();
+  a.first_step = 0.0;
+  a.y0_rows = e->y0_rows;
+  a.t0 = e->t0_d;
+  a.tb0 = e->tb0_d;
+  a.params_rows = e->params_rows;
+  // persistent grid: resident blocks per SM x SMs
+  int nb = 0;
+  ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, m->k_run[0], m->block, m->smem);
+  if (ce != cudaSuccess || nb < 1) {
+    cudaGetLastError();
+    nb = m->kind == NI_KIND_LARGE ? 1 : 4;
+  }
+  e->blocks_per_sm = nb;
+  *out = e;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_set_stream(ni_ensemble *e, void *cuda_stream) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (e->own_stream) cudaStreamDestroy(e->stream);
+  e->stream = (cudaStream_t)cuda_stream;
+  e->own_stream = false;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_set_max_attempts(ni_ensemble *e, int64_t per_launch) {
+  if (!e || per_launch < 1) return fail(NI_ERR_INVALID, "need an ensemble and per_launch >= 1");
+  e->max_attempts = per_launch;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_upload(ni_ensemble *e, const double *t0, int t0_per_traj, const double *y0, const double *params,
+                              const double *t_bound, int t_bound_per_traj) {
+  if (!e || !t0 || !y0 || !t_bound) return fail(NI_ERR_INVALID, "ensemble, t0, y0 and t_bound are required");
+  if (e->mod.P > 0 && !params) return fail(NI_ERR_INVALID, "this right-hand side needs %d parameters per trajectory", e->mod.P);
+  CU(cudaSetDevice(e->device));
+  const size_t N = (size_t)e->N;
+  CU(cudaMemcpyAsync(e->t0_d, t0, sizeof(double) * (t0_per_traj ? N : 1), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->tb0_d, t_bound, sizeof(double) * (t_bound_per_traj ? N : 1), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->y0_rows, y0, sizeof(double) * N * e->mod.n, cudaMemcpyHostToDevice, e->stream));
+  if (e->mod.P > 0)
+    CU(cudaMemcpyAsync(e->params_rows, params, sizeof(double) * N * e->mod.P, cudaMemcpyHostToDevice, e->stream));
+  e->a.t0_stride = t0_per_traj ? 1 : 0;
+  e->a.tb_stride = t_bound_per_traj ? 1 : 0;
+  e->uploaded = true;
+  return NI_OK;
+}
+
+static int launch(ni_ensemble *e, const void *k, int grid, int block, size_t smem) {
+  void *args[] = {(void *)&e->a};
+  CU(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)block), args, smem, e->stream));
+  e->n_launches++;
+  return NI_OK;
+}
+
+static int run_grid(const ni_ensemble *e) {
+  if (e->mod.kind == NI_KIND_LARGE) {
+    long long g = (long long)e->sms * e->blocks_per_sm;
+    return (int)(e->N < g ? e->N : g);
+  }
+  long long need = (e->N + e->mod.block - 1) / e->mod.block;
+  long long cap = (long long)e->sms * e->blocks_per_sm;
+  return (int)(need < cap ? need : cap);
+}
+
+NI_API int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *atol, double max_step, double first_step) {
+  if (!e || !rtol || !atol) return fail(NI_ERR_INVALID, "ensemble, rtol and atol are required");
+  if (!e->uploaded) return fail(NI_ERR_INVALID, "ni_ensemble_upload has not been called");
+  CU(cudaSetDevice(e->device));
+  const int n = e->mod.n;
+  if (e->mod.kind == NI_KIND_SMALL) {
+    for (int i = 0; i < n; ++i) {
+      e->a.rtol[i] = rtol[i];
+      e->a.atol[i] = atol[i];
+    }
+  } else {
+    if (int rc = ni_large_set_tolerances(&e->mod.large, &e->a, rtol, atol, n, e->stream)) return fail(NI_ERR_CUDA, "tolerance upload failed (%d)", rc);
+  }
+  e->a.max_step = max_step;
+  e->a.first_step = first_step;
+  CU(cudaMemsetAsync(e->a.cond_hit, 0, (size_t)e->N, e->stream));
+  CU(cudaMemsetAsync(e->a.rec_cursor, 0, sizeof(unsigned long long), e->stream));
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  int grid;
+  if (e->mod.kind == NI_KIND_LARGE) {
+    grid = run_grid(e);
+  } else {
+    long long need = (e->N + NI_BLOCK - 1) / NI_BLOCK, cap = (long long)e->sms * 16;
+    grid = (int)(need < cap ? need : cap);
+  }
+  if (int rc = launch(e, e->mod.k_init, grid, e->mod.block, e->mod.kind == NI_KIND_LARGE ? e->mod.smem : 0)) return rc;
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  e->have_init_t = true;
+  e->initialised = true;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_sync(ni_ensemble *e) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_init(ni_ensemble *e, const double *t0, int t0_per_traj, const double *y0, const double *params,
+                            const double *t_bound, int t_bound_per_traj, const double *rtol, const double *atol,
+                            double max_step, double first_step) {
+  if (int rc = ni_ensemble_upload(e, t0, t0_per_traj, y0, params, t_bound, t_bound_per_traj)) return rc;
+  if (int rc = ni_ensemble_reset(e, rtol, atol, max_step, first_step)) return rc;
+  return ni_ensemble_sync(e);
+}
+
+// one launch of the run kernel; counters are left in a.queue
+static int launch_run(ni_ensemble *e, int64_t max_accepts, bool timed) {
+  if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
+  e->a.max_accepts = max_accepts;
+  e->a.max_attempts = e->max_attempts;
+  CU(cudaMemsetAsync(e->a.queue, 0, sizeof(unsigned long long) * 8, e->stream));
+  const bool rec = e->a.rec_cap > 0;
+  if (timed) CU(cudaEventRecord(e->ev[2], e->stream));
+  if (int rc = launch(e, e->mod.k_run[rec ? 1 : 0], run_grid(e), e->mod.block, e->mod.smem)) return rc;
+  if (timed) {
+    CU(cudaEventRecord(e->ev[3], e->stream));
+    e->have_run_t = true;
+  }
+  return NI_OK;
+}
+
+static int read_queue(ni_ensemble *e, unsigned long long q[4]) {
+  CU(cudaMemcpyAsync(q, e->a.queue, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_step(ni_ensemble *e, int64_t *n_true) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  if (int rc = launch_run(e, 1, true)) return rc;
+  unsigned long long q[4];
+  if (int rc = read_queue(e, q)) return rc;
+  if (n_true) *n_true = (int64_t)q[3];
+  if (q[1] & NI_FLAG_REC_OVERFLOW) return fail(NI_ERR_REC_OVERFLOW, "record log full (%lld records): drain it and step again", (long long)e->a.rec_cap);
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_run_async(ni_ensemble *e) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  return launch_run(e, 1ll << 62, true);
+}
+
+NI_API int ni_ensemble_run(ni_ensemble *e, int64_t *n_unfinished) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  for (;;) {
+    if (int rc = launch_run(e, 1ll << 62, true)) return rc;
+    unsigned long long q[4];
+    if (int rc = read_queue(e, q)) return rc;
+    if (n_unfinished) *n_unfinished = (int64_t)q[2];
+    if (q[1] & NI_FLAG_REC_OVERFLOW) return fail(NI_ERR_REC_OVERFLOW, "record log full (%lld records): drain it and run again", (long long)e->a.rec_cap);
+    if (q[2] == 0) return NI_OK;  // otherwise max_attempts per launch was exhausted: relaunch
+  }
+}
+
+// ---- small utility kernels (host-facing plumbing, not on the hot path)
+__global__ void ni_k_tbound(NiArgs a, int mode, double t_end, double *saved, unsigned char *flag, const double *newtb) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+    double tb = a.t_bound[i];
+    if (mode == 0) {  // set from array
+      tb = newtb[i];
+    } else if (mode == 1) {  // ff2t begin (_API.py:30-33)
+      saved[i] = tb;
+      const bool not_last = tb > t_end;
+      flag[i] = not_last ? 1 : 0;
+      if (not_last) tb = t_end;
+    } else {  // ff2t end (_API.py:37)
+      tb = saved[i];
+    }
+    a.t_bound[i] = tb;
+    if (a.status[i] == NI_ST_FINISHED && !(a.direction[i] * (a.t[i] - tb) >= 0.0)) a.status[i] = NI_ST_RUNNING;
+  }
+}
+
+// component-major [c][N] <-> row-major [N][c]
+__global__ void ni_k_to_rows(const double *src, double *dst, long long N, int c) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < N * c; k += (long long)gridDim.x * blockDim.x) {
+    const long long i = k / c;
+    const int j = (int)(k - i * c);
+    dst[k] = src[(long long)j * N + i];
+  }
+}
+__global__ void ni_k_rec_rows(const double *src, double *dst, long long count, long long cap, int c) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < count * c; k += (long long)gridDim.x * blockDim.x) {
+    const long long i = k / c;
+    const int j = (int)(k - i * c);
+    dst[k] = src[(long long)j * cap + i];
+  }
+}
+
+static int grid_for(long long work) {
+  long long g = (work + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+NI_API int ni_ensemble_ff2t(ni_ensemble *e, double t_end, uint8_t *is_not_last) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  ni_k_tbound<<<grid_for(e->N), 256, 0, e->stream>>>(e->a, 1, t_end, e->tb_saved, e->flag_d, nullptr);
+  CU(cudaGetLastError());
+  int64_t unfinished = 0;
+  int rc = ni_ensemble_run(e, &unfinished);
+  ni_k_tbound<<<grid_for(e->N), 256, 0, e->stream>>>(e->a, 2, t_end, e->tb_saved, e->flag_d, nullptr);
+  CU(cudaGetLastError());
+  if (is_not_last) CU(cudaMemcpyAsync(is_not_last, e->flag_d, (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return rc;
+}
+
+NI_API int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double value, uint8_t *hit, int64_t *n_hit) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  if (cond_kind < NI_COND_Y_GT || cond_kind > NI_COND_AUX_LT) return fail(NI_ERR_INVALID, "unknown predicate kind %d", cond_kind);
+  const int lim = cond_kind <= NI_COND_Y_LT ? e->mod.n : e->mod.Q;
+  if (index < 0 || index >= lim) return fail(NI_ERR_INVALID, "predicate index %d out of range [0, %d)", index, lim);
+  if (e->mod.kind != NI_KIND_SMALL) return fail(NI_ERR_UNSUPPORTED, "ff2cond is implemented for the thread-per-trajectory kernels only");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemsetAsync(e->a.cond_hit, 0, (size_t)e->N, e->stream));
+  e->a.cond_kind = cond_kind;
+  e->a.cond_index = index;
+  e->a.cond_value = value;
+  int64_t unfinished = 0;
+  int rc = ni_ensemble_run(e, &unfinished);
+  e->a.cond_kind = 0;
+  if (rc != NI_OK) return rc;
+  if (hit || n_hit) {
+    std::vector<uint8_t> tmp;
+    uint8_t *dst = hit;
+    if (!dst) {
+      tmp.resize((size_t)e->N);
+      dst = tmp.data();
+    }
+    CU(cudaMemcpyAsync(dst, e->a.cond_hit, (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (n_hit) {
+      int64_t c = 0;
+      for (int64_t i = 0; i < e->N; ++i) c += dst[i] != 0;
+      *n_hit = c;
+    }
+  }
+  return NI_OK;
+}
+
+struct FieldInfo {
+  void *ptr;
+  int comps;      // components per trajectory
+  size_t elem;    // bytes per element
+  bool is_double;
+};
+
+static bool field_info(ni_ensemble *e, int field, FieldInfo *f) {
+  NiArgs &a = e->a;
+  switch (field) {
+    case NI_F_T: *f = {a.t, 1, 8, true}; return true;
+    case NI_F_Y: *f = {a.y, e->mod.n, 8, true}; return true;
+    case NI_F_AUX: *f = {a.aux, e->mod.Q, 8, true}; return true;
+    case NI_F_H_ABS: *f = {a.h_abs, 1, 8, true}; return true;
+    case NI_F_STEP_SIZE: *f = {a.step_size, 1, 8, true}; return true;
+    case NI_F_KLAST: *f = {a.klast, e->mod.n, 8, true}; return true;
+    case NI_F_STATUS: *f = {a.status, 1, 4, false}; return true;
+    case NI_F_N_ACCEPTED: *f = {a.n_acc, 1, 4, false}; return true;
+    case NI_F_N_REJECTED: *f = {a.n_rej, 1, 4, false}; return true;
+    case NI_F_RUNNING: *f = {a.running, 1, 1, false}; return true;
+    case NI_F_T_BOUND: *f = {a.t_bound, 1, 8, true}; return true;
+    case NI_F_DIRECTION: *f = {a.direction, 1, 8, true}; return true;
+    case NI_F_PARAMS: *f = {a.params, e->mod.P, 8, true}; return true;
+    case NI_F_COND_HIT: *f = {a.cond_hit, 1, 1, false}; return true;
+    default: return false;
+  }
+}
+
+NI_API int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr) {
+  FieldInfo f;
+  if (!e || !dptr || !field_info(e, field, &f)) return fail(NI_ERR_INVALID, "bad ensemble / field %d", field);
+  *dptr = f.ptr;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_get(ni_ensemble *e, int field, void *host_out) {
+  FieldInfo f;
+  if (!e || !host_out || !field_info(e, field, &f)) return fail(NI_ERR_INVALID, "bad ensemble / field %d / NULL buffer", field);
+  CU(cudaSetDevice(e->device));
+  const size_t N = (size_t)e->N;
+  if (f.comps == 0) return NI_OK;
+  if (f.comps > 1 && e->mod.kind == NI_KIND_SMALL) {  // component-major on device -> rows
+    if (int rc = need_scratch(e, N * f.comps * 8)) return rc;
+    ni_k_to_rows<<<grid_for((long long)N * f.comps), 256, 0, e->stream>>>((const double *)f.ptr, (double *)e->scratch, (long long)N, f.comps);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_out, e->scratch, N * f.comps * 8, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    CU(cudaMemcpyAsync(host_out, f.ptr, N * f.comps * f.elem, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in) {
+  if (!e || !host_in) return fail(NI_ERR_INVALID, "ensemble / buffer is NULL");
+  CU(cudaSetDevice(e->device));
+  const size_t N = (size_t)e->N;
+  if (field == NI_F_T_BOUND) {
+    if (int rc = need_scratch(e, N * 8)) return rc;
+    CU(cudaMemcpyAsync(e->scratch, host_in, N * 8, cudaMemcpyHostToDevice, e->stream));
+    ni_k_tbound<<<grid_for(e->N), 256, 0, e->stream>>>(e->a, 0, 0.0, e->tb_saved, e->flag_d, (const double *)e->scratch);
+    CU(cudaGetLastError());
+  } else if (field == NI_F_H_ABS) {
+    CU(cudaMemcpyAsync(e->a.h_abs, host_in, N * 8, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    return fail(NI_ERR_INVALID, "field %d is read-only", field);
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
+// ---- recording
+NI_API int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity) {
+  if (!e || capacity < 0) return fail(NI_ERR_INVALID, "need an ensemble and capacity >= 0");
+  CU(cudaSetDevice(e->device));
+  NiArgs &a = e->a;
+  if (capacity > a.rec_cap) {
+    const size_t c = (size_t)capacity;
+    int rc = NI_OK;
+    if (rc == NI_OK) rc = dalloc(e, &a.rec_traj, c);
+    if (rc == NI_OK) rc = dalloc(e, &a.rec_step, c);
+    if (rc == NI_OK) rc = dalloc(e, &a.rec_t, c);
+    if (rc == NI_OK) rc = dalloc(e, &a.rec_y, c * e->mod.n);
+    if (rc == NI_OK) rc = dalloc(e, &a.rec_aux, c * e->mod.Q);
+    if (rc != NI_OK) {
+      a.rec_cap = 0;
+      return rc;
+    }
+  }
+  a.rec_cap = capacity;
+  CU(cudaMemsetAsync(a.rec_cursor, 0, sizeof(unsigned long long), e->stream));
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_record_count(ni_ensemble *e, int64_t *count) {
+  if (!e || !count) return fail(NI_ERR_INVALID, "ensemble / count is NULL");
+  CU(cudaSetDevice(e->device));
+  unsigned long long c = 0;
+  CU(cudaMemcpyAsync(&c, e->a.rec_cursor, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *count = (int64_t)(c < (unsigned long long)e->a.rec_cap ? c : (unsigned long long)e->a.rec_cap);
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, double *t, double *y, double *aux,
+                                    int64_t max_records, int64_t *n_out) {
+  if (!e || !n_out) return fail(NI_ERR_INVALID, "ensemble / n_out is NULL");
+  int64_t count = 0;
+  if (int rc = ni_ensemble_record_count(e, &count)) return rc;
+  if (count > max_records) return fail(NI_ERR_INVALID, "host buffers hold %lld records, the log has %lld", (long long)max_records, (long long)count);
+  NiArgs &a = e->a;
+  const size_t c = (size_t)count;
+  const int n = e->mod.n, Q = e->mod.Q;
+  if (c > 0) {
+    if (traj) CU(cudaMemcpyAsync(traj, a.rec_traj, c * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (step) CU(cudaMemcpyAsync(step, a.rec_step, c * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (t) CU(cudaMemcpyAsync(t, a.rec_t, c * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (y) {
+      if (e->mod.kind == NI_KIND_SMALL) {
+        if (int rc = need_scratch(e, c * n * 8)) return rc;
+        ni_k_rec_rows<<<grid_for((long long)c * n), 256, 0, e->stream>>>(a.rec_y, (double *)e->scratch, (long long)c, a.rec_cap, n);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(y, e->scratch, c * n * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+      } else {
+        CU(cudaMemcpyAsync(y, a.rec_y, c * n * 8, cudaMemcpyDeviceToHost, e->stream));
+      }
+    }
+    if (aux && Q > 0) {
+      if (e->mod.kind == NI_KIND_SMALL) {
+        if (int rc = need_scratch(e, c * Q * 8)) return rc;
+        ni_k_rec_rows<<<grid_for((long long)c * Q), 256, 0, e->stream>>>(a.rec_aux, (double *)e->scratch, (long long)c, a.rec_cap, Q);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(aux, e->scratch, c * Q * 8, cudaMemcpyDeviceToHost, e->stream));
+      } else {
+        CU(cudaMemcpyAsync(aux, a.rec_aux, c * Q * 8, cudaMemcpyDeviceToHost, e->stream));
+      }
+    }
+  }
+  CU(cudaMemsetAsync(a.rec_cursor, 0, sizeof(unsigned long long), e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *n_out = count;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_timing(ni_ensemble *e, float *ms_init, float *ms_run, int64_t *n_launches) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (ms_init) {
+    *ms_init = -1.f;
+    if (e->have_init_t) CU(cudaEventElapsedTime(ms_init, e->ev[0], e->ev[1]));
+  }
+  if (ms_run) {
+    *ms_run = -1.f;
+    if (e->have_run_t) CU(cudaEventElapsedTime(ms_run, e->ev[2], e->ev[3]));
+  }
+  if (n_launches) *n_launches = e->n_launches;
+  return NI_OK;
+}

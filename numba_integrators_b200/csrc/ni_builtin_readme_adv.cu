@@ -1,0 +1,5 @@
+// Ahead-of-time sm_100a instantiation of the small-system kernels for the built-in RHS "readme_adv".
+#include "ni_rhs_builtin.cuh"
+#include "ni_host.h"
+using NiRhsThis = NiRhsReadmeAdvanced;
+NI_DEFINE_SMALL_KSET(ni_kset_readme_adv, NiRhsThis)

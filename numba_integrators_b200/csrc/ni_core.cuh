@@ -1,0 +1,584 @@
+// ni_core.cuh -- device side of the B200 ODE-ensemble engine (small systems).
+//
+// One thread integrates one trajectory; the RK stage vectors k1..k7 live in
+// registers (every index below is a compile-time constant), the ensemble state
+// is structure-of-arrays in HBM (component-major, stride N) so that loads and
+// stores of a warp are coalesced, and a persistent grid pulls trajectories from
+// an atomic work queue so lanes that finish early are refilled instead of
+// idling (heterogeneous step counts, BASELINE config C4).
+//
+// This header is compiled two ways: ahead of time by nvcc for the built-in
+// right-hand sides (ni_b200.cu) and at load time by NVRTC with a user-supplied
+// RHS snippet.  It therefore includes no host headers.
+//
+// Algorithm (reference = /root/reference/src/numba_integrators):
+//   _basic.py:114-180  _step           -> ni_small_run (attempt loop)
+//   _advanced.py:126-195 step_advanced -> same kernel, ADV = true (h = h_abs*direction)
+//   _basic.py:33-89    select_initial_step -> ni_small_init
+//   _basic.py:203-242  RK.__init__     -> ni_small_init
+//   _aux.py:71-75      norm            -> sequential unfused sum, /n, sqrt
+//   _aux.py:77-115     tableaux        -> NiTab<>
+//   _aux.py:16-19      SAFETY / MIN_FACTOR / MAX_FACTOR
+// Arithmetic order follows SURVEY.md appendix B (what numba + OpenBLAS dgemv
+// produce on the reference host) so that results are bit-identical to the
+// reference wherever `pow` agrees with glibc: tableau contractions are FMA
+// chains in dgemv order, every element-wise expression is unfused
+// (__dmul_rn/__dadd_rn are never contracted, whatever -fmad says).
+#pragma once
+
+#define NI_RK23 0
+#define NI_RK45 1
+
+#define NI_ST_RUNNING 0
+#define NI_ST_FINISHED 1
+#define NI_ST_FAILED 2     // step size fell below 8 ulp(t)   (_basic.py:179-180)
+#define NI_ST_NONFINITE 3  // error norm is NaN (the reference would spin forever)
+
+#define NI_MAX_SMALL_N 16
+#define NI_BLOCK 128
+
+#define NI_FLAG_REC_OVERFLOW 1ull
+
+#define NI_DEV __device__ __forceinline__
+#define NI_HD __host__ __device__
+
+// Kernel arguments (passed by value).  All per-trajectory arrays have N entries;
+// y, klast are [n][N], params [P][N], aux [Q][N].
+struct NiArgs {
+  long long N;
+  double *t, *h_abs, *step_size, *y, *klast, *aux;
+  double *params;
+  double *t_bound, *direction;
+  int *status, *n_acc, *n_rej;
+  unsigned char *running;       // result of the last step() call per trajectory
+  const double *y0_rows;        // init only: N x n row-major
+  const double *t0, *tb0;       // init only: initial time / bound, 1 or N entries
+  int t0_stride, tb_stride;     // 0 (scalar) or 1 (per trajectory)
+  const double *params_rows;    // init only: N x P row-major
+  double max_step, first_step;
+  double rtol[NI_MAX_SMALL_N], atol[NI_MAX_SMALL_N];
+  unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted
+  long long max_attempts;       // per trajectory per launch (bounds kernel time)
+  long long max_accepts;        // 1 = lock-step ni.step(), huge = fast-forward
+  // recording of accepted steps (append log, SoA, capacity rec_cap records)
+  unsigned long long *rec_cursor;
+  long long rec_cap;
+  unsigned int *rec_traj, *rec_step;
+  double *rec_t, *rec_y, *rec_aux;  // rec_y [n][rec_cap], rec_aux [Q][rec_cap]
+  // ff2cond: built-in predicate parameters
+  int cond_kind;                // 0 none, 1 y[i] > c, 2 y[i] < c, 3 aux[i] > c, 4 aux[i] < c
+  int cond_index;
+  double cond_value;
+  unsigned char *cond_hit;
+};
+
+// ---------------------------------------------------------------- utilities
+template <int I>
+struct NiInt {
+  static constexpr int value = I;
+};
+template <int B, int E, class F>
+NI_DEV void ni_static_for(F &&f) {
+  if constexpr (B < E) {
+    f(NiInt<B>{});
+    ni_static_for<B + 1, E>(f);
+  }
+}
+
+// ---------------------------------------------------------------- tableaux
+// Same rational expressions as _aux.py:77-115, folded in IEEE double at compile time.
+template <int METHOD>
+struct NiTab;
+
+template <>
+struct NiTab<NI_RK23> {
+  static constexpr int S = 3;
+  static constexpr int ORDER = 2;
+  NI_HD static constexpr double a(int s, int j) {
+    return s == 1 ? (j == 0 ? 1.0 / 2 : 0.0) : s == 2 ? (j == 1 ? 3.0 / 4 : 0.0) : 0.0;
+  }
+  NI_HD static constexpr double b(int j) { return j == 0 ? 2.0 / 9 : j == 1 ? 1.0 / 3 : j == 2 ? 4.0 / 9 : 0.0; }
+  NI_HD static constexpr double c(int j) { return j == 1 ? 1.0 / 2 : j == 2 ? 3.0 / 4 : 0.0; }
+  NI_HD static constexpr double e(int j) {
+    return j == 0 ? 5.0 / 72 : j == 1 ? -1.0 / 12 : j == 2 ? -1.0 / 9 : j == 3 ? 1.0 / 8 : 0.0;
+  }
+};
+
+template <>
+struct NiTab<NI_RK45> {
+  static constexpr int S = 6;
+  static constexpr int ORDER = 4;
+  NI_HD static constexpr double a(int s, int j) {
+    switch (s * 8 + j) {
+      case 1 * 8 + 0: return 1.0 / 5;
+      case 2 * 8 + 0: return 3.0 / 40;
+      case 2 * 8 + 1: return 9.0 / 40;
+      case 3 * 8 + 0: return 44.0 / 45;
+      case 3 * 8 + 1: return -56.0 / 15;
+      case 3 * 8 + 2: return 32.0 / 9;
+      case 4 * 8 + 0: return 19372.0 / 6561;
+      case 4 * 8 + 1: return -25360.0 / 2187;
+      case 4 * 8 + 2: return 64448.0 / 6561;
+      case 4 * 8 + 3: return -212.0 / 729;
+      case 5 * 8 + 0: return 9017.0 / 3168;
+      case 5 * 8 + 1: return -355.0 / 33;
+      case 5 * 8 + 2: return 46732.0 / 5247;
+      case 5 * 8 + 3: return 49.0 / 176;
+      case 5 * 8 + 4: return -5103.0 / 18656;
+      default: return 0.0;
+    }
+  }
+  NI_HD static constexpr double b(int j) {
+    switch (j) {
+      case 0: return 35.0 / 384;
+      case 2: return 500.0 / 1113;
+      case 3: return 125.0 / 192;
+      case 4: return -2187.0 / 6784;
+      case 5: return 11.0 / 84;
+      default: return 0.0;
+    }
+  }
+  NI_HD static constexpr double c(int j) {
+    switch (j) {
+      case 1: return 1.0 / 5;
+      case 2: return 3.0 / 10;
+      case 3: return 4.0 / 5;
+      case 4: return 8.0 / 9;
+      case 5: return 1.0;
+      default: return 0.0;
+    }
+  }
+  NI_HD static constexpr double e(int j) {
+    switch (j) {
+      case 0: return -71.0 / 57600;
+      case 2: return 71.0 / 16695;
+      case 3: return -71.0 / 1920;
+      case 4: return 17253.0 / 339200;
+      case 5: return -22.0 / 525;
+      case 6: return 1.0 / 40;
+      default: return 0.0;
+    }
+  }
+};
+
+// Coefficient of row ROW, column j.  ROW in 1..S-1 -> A[ROW][j]; ROW == S -> B[j]; ROW == S+1 -> E[j].
+template <int METHOD, int ROW>
+NI_HD constexpr double ni_coef(int j) {
+  using T = NiTab<METHOD>;
+  return ROW < T::S ? T::a(ROW, j) : ROW == T::S ? T::b(j) : T::e(j);
+}
+
+// fma(x, c, acc) with the structural zeros of the tableau skipped (fma(x, 0, acc) == acc for
+// finite x; the reference does not skip them, the results differ only for non-finite x).
+template <int METHOD, int ROW, int J>
+NI_DEV double ni_fma_term(double x, double acc) {
+  constexpr double c = ni_coef<METHOD, ROW>(J);
+  if constexpr (c == 0.0)
+    return acc;
+  else
+    return fma(x, c, acc);
+}
+// fma(xi, ci, rn(xj*cj)): the seed pair of the dgemv order
+template <int METHOD, int ROW, int I, int J>
+NI_DEV double ni_pair(double xi, double xj) {
+  constexpr double ci = ni_coef<METHOD, ROW>(I), cj = ni_coef<METHOD, ROW>(J);
+  if constexpr (ci == 0.0 && cj == 0.0)
+    return 0.0;
+  else if constexpr (cj == 0.0)
+    return __dmul_rn(xi, ci);
+  else if constexpr (ci == 0.0)
+    return __dmul_rn(xj, cj);
+  else
+    return fma(xi, ci, __dmul_rn(xj, cj));
+}
+
+// out[i] = sum_{j<COLS} K[j][i] * coef(j) in the order OpenBLAS dgemv_n uses for an (n x COLS)
+// matrix with n <= 3 rows (oracle/ni_oracle.c:dot_cols is the CPU twin).
+template <int METHOD, int ROW, int COLS, int n, int KR>
+NI_DEV void ni_dot(const double (&K)[KR][n], double (&out)[n]) {
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    double acc;
+    if constexpr (COLS <= 3) {
+      acc = 0.0;
+      bool first = true;
+      ni_static_for<0, COLS>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        constexpr double c = ni_coef<METHOD, ROW>(j);
+        if constexpr (c != 0.0) {
+          acc = first ? __dmul_rn(K[j][i], c) : fma(K[j][i], c, acc);
+          first = false;
+        }
+      });
+    } else {
+      if constexpr (n == 1) {
+        acc = __dmul_rn(K[1][i], ni_coef<METHOD, ROW>(1));
+        acc = ni_fma_term<METHOD, ROW, 0>(K[0][i], acc);
+        acc = ni_fma_term<METHOD, ROW, 2>(K[2][i], acc);
+        acc = ni_fma_term<METHOD, ROW, 3>(K[3][i], acc);
+      } else {
+        acc = __dadd_rn(ni_pair<METHOD, ROW, 0, 1>(K[0][i], K[1][i]), ni_pair<METHOD, ROW, 2, 3>(K[2][i], K[3][i]));
+      }
+      ni_static_for<4, COLS>([&](auto jj) {
+        constexpr int j = decltype(jj)::value;
+        acc = ni_fma_term<METHOD, ROW, j>(K[j][i], acc);
+      });
+    }
+    out[i] = acc;
+  }
+}
+
+// _aux.py:71-75
+template <int n>
+NI_DEV double ni_rms(const double (&x)[n]) {
+  double acc = __dmul_rn(x[0], x[0]);
+#pragma unroll
+  for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(x[i], x[i]));
+  return sqrt(acc / (double)n);
+}
+
+NI_DEV double ni_pow(double x, double e) { return pow(x, e); }
+
+// |nextafter(t, dir*inf) - t|  (_basic.py:139), for finite t
+NI_DEV double ni_ulp_eps(double t, double dir) {
+  double nx;
+  if (t == 0.0) {
+    nx = __longlong_as_double(dir > 0.0 ? 1LL : (long long)0x8000000000000001ULL);
+  } else {
+    const long long b = __double_as_longlong(t);
+    nx = __longlong_as_double(((t > 0.0) == (dir > 0.0)) ? b + 1 : b - 1);
+  }
+  return fabs(__dadd_rn(nx, -t));
+}
+
+// ---------------------------------------------------------------- predicates (ff2cond)
+template <int n, int Q>
+NI_DEV bool ni_cond_test(const NiArgs &a, const double (&y)[n], const double *aux) {
+  if (a.cond_kind == 0) return false;
+  double v = 0.0;
+  if (a.cond_kind <= 2) {
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+      if (i == a.cond_index) v = y[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+      if (i == a.cond_index) v = aux[i];
+  }
+  return (a.cond_kind & 1) ? v > a.cond_value : v < a.cond_value;
+}
+
+// ---------------------------------------------------------------- init kernel
+// RK.__init__ (_basic.py:203-242): FSAL seed K[-1] = f(t0, y0), direction, error exponent,
+// select_initial_step (_basic.py:33-89) unless first_step is given.  Also transposes the
+// row-major host layout into the component-major device layout.
+template <class Rhs, int METHOD>
+NI_DEV void ni_small_init_body(const NiArgs &a) {
+  constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
+  constexpr double err_exp = -1.0 / (NiTab<METHOD>::ORDER + 1);
+  const long long N = a.N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < N;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double y[n], f0[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
+#pragma unroll
+    for (int i = 0; i < n; ++i) y[i] = a.y0_rows[idx * n + i];
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = a.params_rows[idx * P + i];
+    const double t0 = a.t0[idx * a.t0_stride], tb = a.tb0[idx * a.tb_stride];
+    Rhs::eval(t0, y, p, f0, aux);
+    const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
+    double h_abs;
+    if (a.first_step == 0.0) {
+      double scale[n], tmp[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) scale[i] = fma(fabs(y[i]), a.rtol[i], a.atol[i]);
+#pragma unroll
+      for (int i = 0; i < n; ++i) tmp[i] = y[i] / scale[i];
+      const double d0 = ni_rms<n>(tmp);
+#pragma unroll
+      for (int i = 0; i < n; ++i) tmp[i] = f0[i] / scale[i];
+      const double d1 = ni_rms<n>(tmp);
+      const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : __dmul_rn(0.01, d0) / d1;
+      const double hd = __dmul_rn(h0, dir);
+      double y1[n], f1[n], auxd[Q > 0 ? Q : 1];
+#pragma unroll
+      for (int i = 0; i < n; ++i) y1[i] = fma(hd, f0[i], y[i]);
+      Rhs::eval(__dadd_rn(t0, hd), y1, p, f1, auxd);
+#pragma unroll
+      for (int i = 0; i < n; ++i) tmp[i] = __dadd_rn(f1[i], -f0[i]) / scale[i];
+      const double d2 = ni_rms<n>(tmp) / h0;
+      double h1;
+      if (d1 <= 1e-15 && d2 <= 1e-15)
+        h1 = fmax(1e-6, __dmul_rn(h0, 1e-3));
+      else
+        h1 = ni_pow(__dmul_rn(fmax(d1, d2), 100.0), err_exp);
+      h_abs = fmin(__dmul_rn(100.0, h0), h1);
+    } else {
+      h_abs = fabs(a.first_step);
+    }
+    a.t[idx] = t0;
+    a.t_bound[idx] = tb;
+    a.direction[idx] = dir;
+    a.h_abs[idx] = h_abs;
+    a.step_size[idx] = __dmul_rn(dir, h_abs);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      a.y[i * N + idx] = y[i];
+      a.klast[i * N + idx] = f0[i];
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) a.params[i * N + idx] = p[i];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
+    a.status[idx] = NI_ST_RUNNING;
+    a.n_acc[idx] = 0;
+    a.n_rej[idx] = 0;
+    a.running[idx] = 1;
+  }
+}
+
+// ---------------------------------------------------------------- run kernel
+// Persistent grid; every lane owns one trajectory at a time and performs one step ATTEMPT per
+// loop iteration (accept/reject only changes which values are committed, so a warp never
+// diverges inside the stage loop).  A lane retires its trajectory when it finished, failed,
+// used up max_accepts / max_attempts, hit the ff2cond predicate or found the record log full;
+// it then pulls the next trajectory index from the queue.
+template <class Rhs, int METHOD, bool ADV, bool REC>
+NI_DEV void ni_small_run_body(const NiArgs &a) {
+  constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
+  using Tab = NiTab<METHOD>;
+  constexpr int S = Tab::S;
+  constexpr double err_exp = -1.0 / (Tab::ORDER + 1);  // _basic.py:234
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long N = a.N;
+  const unsigned lane = threadIdx.x & 31u;
+
+  long long idx = 0;
+  bool active = false, exhausted = false, fresh = true, last_accept = false;
+  double t = 0, h_abs = 0, tb = 0, dir = 1, eps = 0, min_step = 0, step_h = 0;
+  double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
+  int nacc = 0, nrej = 0, status = NI_ST_RUNNING;
+  long long att_left = 0, acc_left = 0;
+
+  auto retire = [&]() {
+    a.t[idx] = t;
+    a.h_abs[idx] = h_abs;
+    a.step_size[idx] = step_h;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      a.y[i * N + idx] = y[i];
+      a.klast[i * N + idx] = kl[i];
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
+    a.status[idx] = status;
+    a.n_acc[idx] = nacc;
+    a.n_rej[idx] = nrej;
+    a.running[idx] = last_accept ? 1 : 0;
+    if (status == NI_ST_RUNNING) atomicAdd(a.queue + 2, 1ull);
+    if (last_accept) atomicAdd(a.queue + 3, 1ull);
+    active = false;
+  };
+
+  for (;;) {
+    // ---- refill: pull the next trajectory (warp-aggregated queue pop)
+    if (!active && !exhausted) {
+      const unsigned need = __activemask();
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
+      base = __shfl_sync(need, base, leader);
+      idx = (long long)(base + __popc(need & ((1u << lane) - 1u)));
+      if (idx >= N || (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW))) {
+        exhausted = true;
+      } else {
+        status = a.status[idx];
+        if (status == NI_ST_RUNNING) {
+          t = a.t[idx];
+          h_abs = a.h_abs[idx];
+          step_h = a.step_size[idx];
+          tb = a.t_bound[idx];
+          dir = a.direction[idx];
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y[i] = a.y[i * N + idx];
+            kl[i] = a.klast[i * N + idx];
+          }
+#pragma unroll
+          for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
+#pragma unroll
+          for (int i = 0; i < Q; ++i) aux[i] = a.aux[i * N + idx];
+          nacc = a.n_acc[idx];
+          nrej = a.n_rej[idx];
+          att_left = a.max_attempts;
+          acc_left = a.max_accepts;
+          fresh = true;
+          last_accept = false;
+          active = true;
+        } else {
+          a.running[idx] = 0;  // step() on a finished / failed solver returns False
+        }
+      }
+    }
+    if (__all_sync(FULL, !active && exhausted)) break;
+
+    // ---- step entry (_basic.py:135-143)
+    if (active && fresh) {
+      if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached
+        step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
+        status = NI_ST_FINISHED;
+        last_accept = false;
+        retire();
+      } else {
+        eps = ni_ulp_eps(t, dir);
+        min_step = __dmul_rn(8.0, eps);
+        if (h_abs < min_step) h_abs = min_step;
+        fresh = false;
+      }
+    }
+
+    // ---- one attempt (_basic.py:145-169)
+    bool ok = false;
+    double tn = 0, h = 0, h_pre = 0, en = 0;
+    double K[S + 1][n], yn[n], auxn[Q > 0 ? Q : 1];
+    if (active) {
+      h_pre = h_abs;
+      if (h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+      h = ADV ? __dmul_rn(h_abs, dir) : h_abs;
+      tn = __dadd_rn(t, h);
+#pragma unroll
+      for (int i = 0; i < n; ++i) K[0][i] = kl[i];  // K[0] = K[-1]: stale after a rejection
+      if (__dmul_rn(dir, __dadd_rn(tn, -tb)) >= 0.0) {
+        tn = tb;
+        h = __dadd_rn(tn, -t);
+        h_abs = fabs(h);
+      }
+      ni_static_for<1, S>([&](auto ss) {
+        constexpr int s = decltype(ss)::value;
+        double d[n], ys[n], auxd[Q > 0 ? Q : 1];
+        ni_dot<METHOD, s, s, n>(K, d);
+#pragma unroll
+        for (int i = 0; i < n; ++i) ys[i] = __dadd_rn(y[i], __dmul_rn(d[i], h));
+        Rhs::eval(__dadd_rn(t, __dmul_rn(Tab::c(s), h)), ys, p, K[s], auxd);
+      });
+      {
+        double d[n];
+        ni_dot<METHOD, S, S, n>(K, d);
+#pragma unroll
+        for (int i = 0; i < n; ++i) yn[i] = __dadd_rn(y[i], __dmul_rn(h, d[i]));
+        Rhs::eval(tn, yn, p, K[S], auxn);
+        double ev[n];
+        ni_dot<METHOD, S + 1, S + 1, n>(K, ev);
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+          ev[i] = __dmul_rn(ev[i], h) / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+        en = ni_rms<n>(ev);
+      }
+      ok = en < 1.0;
+      --att_left;
+    }
+
+    // ---- record log: reserve one slot per accepting lane (warp-aggregated append)
+    long long slot = -1;
+    if (REC) {
+      const unsigned m = __ballot_sync(FULL, ok);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(a.rec_cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (ok) slot = (long long)(base + __popc(m & ((1u << lane) - 1u)));
+      }
+    }
+
+    // ---- controller + commit (_basic.py:171-180)
+    if (active) {
+      if (ok) {
+        if (REC && slot >= a.rec_cap) {
+          // log full: undo this attempt and park the trajectory (restartable: the state before
+          // an attempt is exactly t, y, h_abs, K[-1])
+          atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+          h_abs = h_pre;
+          ++att_left;
+          last_accept = false;
+          retire();
+        } else {
+          const double fac = (en == 0.0) ? 10.0 : fmin(10.0, __dmul_rn(0.9, ni_pow(en, err_exp)));
+          h_abs = __dmul_rn(h_abs, fac);
+          t = tn;
+          step_h = h;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            y[i] = yn[i];
+            kl[i] = K[S][i];
+          }
+#pragma unroll
+          for (int i = 0; i < Q; ++i) aux[i] = auxn[i];
+          ++nacc;
+          --acc_left;
+          fresh = true;
+          last_accept = true;
+          if (REC) {
+            const long long c = a.rec_cap;
+            a.rec_traj[slot] = (unsigned int)idx;
+            a.rec_step[slot] = (unsigned int)nacc;
+            a.rec_t[slot] = t;
+#pragma unroll
+            for (int i = 0; i < n; ++i) a.rec_y[i * c + slot] = y[i];
+#pragma unroll
+            for (int i = 0; i < Q; ++i) a.rec_aux[i * c + slot] = aux[i];
+          }
+          bool hit = false;
+          if (a.cond_kind != 0) {
+            hit = ni_cond_test<n, Q>(a, y, aux);
+            if (hit) a.cond_hit[idx] = 1;
+          }
+          if (hit || acc_left <= 0 || att_left <= 0) {
+            retire();
+          } else if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
+            // fast-forward: the terminal step() call of `while step(): pass`
+            step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
+            status = NI_ST_FINISHED;
+            last_accept = false;
+            retire();
+          }
+        }
+      } else if (!(en >= 1.0)) {
+        ++nrej;
+        status = NI_ST_NONFINITE;
+        step_h = h;
+        last_accept = false;
+        retire();
+      } else {
+        const double fac = fmax(0.2, __dmul_rn(0.9, ni_pow(en, err_exp)));
+        h_abs = __dmul_rn(h_abs, fac);
+        ++nrej;
+#pragma unroll
+        for (int i = 0; i < n; ++i) kl[i] = K[S][i];
+        last_accept = false;
+        if (h_abs < min_step) {  // too small a step: the reference commits the REJECTED t, y
+          t = tn;
+          step_h = h;
+#pragma unroll
+          for (int i = 0; i < n; ++i) y[i] = yn[i];
+#pragma unroll
+          for (int i = 0; i < Q; ++i) aux[i] = auxn[i];
+          status = NI_ST_FAILED;
+          retire();
+        } else if (att_left <= 0) {
+          retire();
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernel entry points
+template <class Rhs, int METHOD>
+__global__ void __launch_bounds__(NI_BLOCK) ni_k_init(const NiArgs a) {
+  ni_small_init_body<Rhs, METHOD>(a);
+}
+template <class Rhs, int METHOD, bool ADV, bool REC>
+__global__ void __launch_bounds__(NI_BLOCK) ni_k_run(const NiArgs a) {
+  ni_small_run_body<Rhs, METHOD, ADV, REC>(a);
+}

@@ -1,0 +1,105 @@
+// ni_rhs_builtin.cuh -- built-in right-hand sides for the small-system kernels.
+//
+// Each functor: N (state dim), P (parameters per trajectory), Q (auxiliary outputs) and
+//   eval(t, y[N], p[P], dy[N], aux[Q]).
+// The expression order (and the absence of FMA contraction: __dmul_rn/__dadd_rn) is the
+// same as in oracle/ni_oracle.c:rhs_eval and in the numba functions oracle/gen_golden.py
+// hands to the reference, so that all three produce identical bits.
+#pragma once
+#include "ni_core.cuh"
+
+#define NI_RHS_HARMONIC 0
+#define NI_RHS_LORENZ63 1
+#define NI_RHS_VANDERPOL 2
+#define NI_RHS_HEAT1D 3
+#define NI_RHS_BURGERS1D 4
+#define NI_RHS_EXPONENTIAL 5
+#define NI_RHS_RICCATI 6
+#define NI_RHS_README_ADV 7
+#define NI_RHS_BLOWUP 8
+#define NI_RHS_COUNT 9
+
+#define NI_SUB(a, b) __dadd_rn((a), -(b))
+#define NI_ADD(a, b) __dadd_rn((a), (b))
+#define NI_MUL(a, b) __dmul_rn((a), (b))
+
+// y0' = y1, y1' = -y0   (reference.py:46-49 "sine", README.md:54-57)
+struct NiRhsHarmonic {
+  static constexpr int N = 2, P = 0, Q = 0;
+  NI_DEV static void eval(double, const double *y, const double *, double *dy, double *) {
+    dy[0] = y[1];
+    dy[1] = -y[0];
+  }
+};
+
+// Lorenz-63, p = (sigma, rho, beta), aux = x^2 + y^2 + z^2
+struct NiRhsLorenz63 {
+  static constexpr int N = 3, P = 3, Q = 1;
+  NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *aux) {
+    const double x = y[0], yy = y[1], z = y[2];
+    dy[0] = NI_MUL(p[0], NI_SUB(yy, x));
+    dy[1] = NI_SUB(NI_MUL(x, NI_SUB(p[1], z)), yy);
+    dy[2] = NI_SUB(NI_MUL(x, yy), NI_MUL(p[2], z));
+    aux[0] = NI_ADD(NI_ADD(NI_MUL(x, x), NI_MUL(yy, yy)), NI_MUL(z, z));
+  }
+};
+
+// Van der Pol, p = (mu)
+struct NiRhsVanDerPol {
+  static constexpr int N = 2, P = 1, Q = 0;
+  NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *) {
+    dy[0] = y[1];
+    dy[1] = NI_SUB(NI_MUL(NI_MUL(p[0], NI_SUB(1.0, NI_MUL(y[0], y[0]))), y[1]), y[0]);
+  }
+};
+
+// y' = y   (reference.py:54-57), any small N
+template <int N_>
+struct NiRhsExponential {
+  static constexpr int N = N_, P = 0, Q = 0;
+  NI_DEV static void eval(double, const double *y, const double *, double *dy, double *) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dy[i] = y[i];
+  }
+};
+
+// y' = 2y/x - x^2 y^2   (reference.py:38-41)
+struct NiRhsRiccati {
+  static constexpr int N = 1, P = 0, Q = 0;
+  NI_DEV static void eval(double t, const double *y, const double *, double *dy, double *) {
+    dy[0] = NI_SUB(NI_MUL(2.0, y[0]) / t, NI_MUL(NI_MUL(t, t), NI_MUL(y[0], y[0])));
+  }
+};
+
+// README.md:80-85 Advanced example: p = (a, b0, b1); aux = a*y1; dy = (aux + b0, -y0 + b1)
+struct NiRhsReadmeAdvanced {
+  static constexpr int N = 2, P = 3, Q = 1;
+  NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *aux) {
+    const double a = NI_MUL(p[0], y[1]);
+    dy[0] = NI_ADD(a, p[1]);
+    dy[1] = NI_ADD(-y[0], p[2]);
+    aux[0] = a;
+  }
+};
+
+// y' = y^2 (finite-time blow-up: exercises the step-too-small exit, _basic.py:179-180)
+struct NiRhsBlowup {
+  static constexpr int N = 1, P = 0, Q = 0;
+  NI_DEV static void eval(double, const double *y, const double *, double *dy, double *) {
+    dy[0] = NI_MUL(y[0], y[0]);
+  }
+};
+
+// Small method-of-lines heat / Burgers systems (N <= NI_MAX_SMALL_N) in registers; the
+// large-dimension versions live in ni_large.cuh.
+template <int N_>
+struct NiRhsHeatSmall {
+  static constexpr int N = N_, P = 1, Q = 0;
+  NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double ym = j > 0 ? y[j - 1] : 0.0, yp = j + 1 < N ? y[j + 1] : 0.0;
+      dy[j] = NI_MUL(p[0], NI_ADD(NI_SUB(ym, NI_MUL(2.0, y[j])), yp));
+    }
+  }
+};
