@@ -1,0 +1,338 @@
+"""Headline benchmark: accepted trajectory-steps/s of the batched adaptive RK integrator.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--traj M] [--impl reference]
+
+One "step" integrates the whole ensemble shard of this GPU from t0 to t_bound: the init kernel
+(FSAL seed + select_initial_step, inputs already resident in HBM) followed by ONE launch of the
+persistent fast-forward kernel.  `value` is the whole-job aggregate (all ranks' accepted steps /
+max-over-ranks device time); `e2e` repeats the measurement through the C ABI with pinned HOST
+buffers (upload -> reset -> run -> download of terminal t, y, aux, counters) inside the timed
+region.  Weak scaling: every rank integrates its own --traj trajectories.
+
+The CPU oracle (oracle/) is used only as the reported baseline (`cpu_baseline`, `--impl reference`)
+-- never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'accepted_trajectory_steps_per_s'
+UNIT = 'steps/s'
+DEFAULT_TRAJ = {'c2': 1_000_000, 'c3': 10_000_000, 'c4': 4_000_000, 'c5': 16_384}
+
+
+def make_workload(name, traj, shard, n_shards, t_bound):
+    from numba_integrators_b200 import workloads as wl
+    kw = {} if t_bound is None else {'t_bound': t_bound}
+    if name == 'c2':
+        return wl.c2_harmonic(N=traj, shard=shard, **kw)
+    if name == 'c3':
+        return wl.c3_lorenz(N=traj, shard=shard, **kw)
+    if name == 'c4':
+        return wl.c4_vanderpol(N=traj, shard=shard, n_shards=n_shards, **kw)
+    if name == 'c5':
+        return wl.c5_heat(N=traj, shard=shard, **kw)
+    raise SystemExit(f'unknown workload {name}')
+
+
+def workload_label(w, traj):
+    return (f'{w.name}: {traj} trajectories/GPU, {w.method}, n={w.n}, t_bound={w.t_bound:g}, atol=rtol={w.rtol:g}'
+            + (', via ni.Advanced (per-trajectory parameters, auxiliary output)' if w.advanced else ''))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_oracle_rate(w, seconds, threads=0):
+    """Oracle port on the host cores over a bounded prefix sample of the workload; ~`seconds` of work."""
+    from oracle import oracle as orc
+    method = orc.RK45 if w.method == 'RK45' else orc.RK23
+    threads = threads or orc.max_threads()
+    n = min(w.N, max(threads * 8, 256 if w.n < 64 else threads))
+
+    def run(k):
+        t0 = time.perf_counter()
+        o = orc.run_ensemble(w.rhs, method, w.t0, w.y0[:k], w.t_bound, params=None if w.params is None else w.params[:k],
+                             rtol=w.rtol, atol=w.atol, advanced=w.advanced, nthreads=threads)
+        return time.perf_counter() - t0, int(o['n_accepted'].sum())
+
+    dt, acc = run(n)  # calibration (also warms caches)
+    k = int(min(w.N, max(n, n * seconds / max(dt, 1e-3))))
+    dt, acc = run(k)
+    return acc / dt, k, threads, dt
+
+
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's algorithm on the host cores (oracle port; the reference itself is
+    Python+numba and cannot travel to the GPU box).  Rank 0 only."""
+    if rank != 0:
+        return
+    w = make_workload(args.workload, min(args.traj, 2_000_000 if args.workload != 'c5' else 512), 0, 1, args.t_bound)
+    # size one step at ~args.cpu_seconds / steps of CPU work
+    per_step = max(1.0, args.cpu_seconds / max(args.steps, 1))
+    rate, k, threads, _ = cpu_oracle_rate(w, per_step)
+    from oracle import oracle as orc
+    method = orc.RK45 if w.method == 'RK45' else orc.RK23
+
+    def one():
+        t0 = time.perf_counter()
+        o = orc.run_ensemble(w.rhs, method, w.t0, w.y0[:k], w.t_bound, params=None if w.params is None else w.params[:k],
+                             rtol=w.rtol, atol=w.atol, advanced=w.advanced, nthreads=threads)
+        return time.perf_counter() - t0, int(o['n_accepted'].sum())
+
+    for _ in range(args.warmup):
+        one()
+    tot_t, tot_acc = 0.0, 0
+    for _ in range(args.steps):
+        dt, acc = one()
+        tot_t += dt
+        tot_acc += acc
+    value = tot_acc / tot_t
+    sample = f'first {k} trajectories of the workload per step, oracle C port, {threads} host threads'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload_label(w, args.traj), 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(DEFAULT_TRAJ))
+    ap.add_argument('--traj', type=int, default=0, help='trajectories per GPU (default: the BASELINE config size)')
+    ap.add_argument('--t-bound', type=float, default=None)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.traj = args.traj or DEFAULT_TRAJ[args.workload]
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import numba_integrators_b200 as ni
+    from numba_integrators_b200 import _lib
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = make_workload(args.workload, args.traj, rank, world, args.t_bound)
+    N, n = w.N, w.n
+    f = ni.BuiltinRHS(w.rhs)
+    ctor_kw = dict(rtol=w.rtol, atol=w.atol, device=local)
+    record = args.workload == 'c2'
+    if w.advanced:
+        Solver = ni.Advanced(f.P, f.Q, ni.RK45 if w.method == 'RK45' else ni.RK23)
+        ens = Solver(f, w.t0, w.y0, w.params, w.t_bound, **ctor_kw)
+    else:
+        ctor = ni.RK45 if w.method == 'RK45' else ni.RK23
+        ens = ctor(f(*w.params.T) if f.P else f, w.t0, w.y0, w.t_bound, **ctor_kw)
+    stream = torch.cuda.current_stream()
+    ens.set_stream(stream.cuda_stream)
+    if record:
+        ens.record_enable(int(N * 1000))
+
+    # measured FP64 peak (MEASURED_PEAKS.json has HBM and bf16 only)
+    pk = _lib.C.c_double(0)
+    _lib.check(_lib.lib().ni_fp64_peak(local, 2000, 3, pk))
+    fp64_peak = pk.value
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())
+    except OSError:
+        pass
+
+    def one_step():
+        ens.reset()
+        ens.run_async()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    launches0 = ens.timing()['launches']
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        ens.reset()
+        kev[i][0].record()
+        ens.run_async()
+        kev[i][1].record()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    run_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    launches = ens.timing()['launches'] - launches0
+    acc = ens.n_accepted.astype(np.int64)
+    rej = ens.n_rejected.astype(np.int64)
+    status = ens.status
+    assert np.all(status == _lib.ST_FINISHED), f'{np.sum(status != _lib.ST_FINISHED)} trajectories did not finish'
+    acc_rank, att_rank = int(acc.sum()), int(acc.sum() + rej.sum())
+
+    tms = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    tot = torch.tensor([acc_rank, att_rank], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max = float(tms.item())
+    acc_all = float(tot[0].item())
+    value = acc_all * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        P, Q = ens.P, ens.Q
+        y0_h = torch.from_numpy(w.y0).pin_memory()
+        par_h = torch.from_numpy(w.params).pin_memory() if P else None
+        out = {
+            _lib.F_T: torch.empty(N, dtype=torch.float64).pin_memory(),
+            _lib.F_Y: torch.empty((N, n), dtype=torch.float64).pin_memory(),
+            _lib.F_N_ACCEPTED: torch.empty(N, dtype=torch.int32).pin_memory(),
+            _lib.F_N_REJECTED: torch.empty(N, dtype=torch.int32).pin_memory(),
+            _lib.F_STATUS: torch.empty(N, dtype=torch.int32).pin_memory(),
+        }
+        if Q:
+            out[_lib.F_AUX] = torch.empty((N, Q), dtype=torch.float64).pin_memory()
+        h2d = y0_h.numel() * 8 + (par_h.numel() * 8 if P else 0) + 16
+        d2h = sum(t.numel() * t.element_size() for t in out.values())
+
+        def e2e_step():
+            ens.upload(w.t0, y0_h, par_h, w.t_bound)
+            ens.reset()
+            ens.run_async()
+            for fld, buf in out.items():
+                ens.fetch(fld, buf)
+
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        tms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tms2, op=dist.ReduceOp.MAX)
+        acc_e2e = int(out[_lib.F_N_ACCEPTED].numpy().astype(np.int64).sum())
+        assert acc_e2e == acc_rank, (acc_e2e, acc_rank)
+        e2e = {'value': acc_all * args.steps / (float(tms2.item()) * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': float(tms2.item()) / args.steps,
+               'path': 'ni_ensemble_upload(pinned) -> ni_ensemble_reset -> ni_ensemble_run_async -> ni_ensemble_get x%d' % len(out)}
+
+    if rank == 0:
+        flops = w.flops_per_attempt * att_rank  # algorithmic flops of one launch
+        achieved = flops / (run_ms * 1e-3) / 1e12
+        roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                    'frac': achieved / fp64_peak if fp64_peak else None, 'traffic': None,
+                    'kernel': 'ni_k_run (persistent fast-forward kernel)', 'kernel_ms': run_ms,
+                    'flops_per_attempt': w.flops_per_attempt, 'attempts_per_launch': att_rank,
+                    'peak_source': 'live DFMA-chain microbenchmark ni_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; '
+                                   'nominal 37.2 TFLOP/s)',
+                    'hbm_gbs_measured': peaks.get('hbm_gbs')}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': workload_label(w, args.traj), 'parallelism': f'{world} GPU(s), trajectories '
+                           'sharded by index, no data-path collective',
+                           'l2': f'inputs {N * (n + ens.P) * 8 / 1e6:.0f} MB + state per launch exceed the 126 MB L2',
+                           'accepted_per_traj': acc_rank / N, 'rejected_per_traj': (att_rank - acc_rank) / N},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, k, threads, dt = cpu_oracle_rate(w, args.cpu_seconds)
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                    'sample': f'first {k} trajectories of the same workload, {dt:.1f} s, oracle C port '
+                                              f'of the reference algorithm on {threads} host threads'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -148,6 +148,10 @@ int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, dou
 /* device time of the most recent init / run kernels (CUDA events on the ensemble's stream) */
 int ni_ensemble_timing(ni_ensemble *e, float *ms_init, float *ms_run, int64_t *n_launches);
 
+/* measured FP64 (DFMA) peak of `device` in TFLOP/s: register-resident FMA chains, best of
+ * `repeats` launches of `iters` x 128 FMAs per thread (roofline denominator for bench.py). */
+int ni_fp64_peak(int device, int iters, int repeats, double *tflops_best);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,7 +71,7 @@ class StepMask(np.ndarray):
     """Per-trajectory bool result of step()/ff2t() on an ensemble; truthy while ANY trajectory is."""
 
     def __bool__(self):
-        return bool(self.any())
+        return bool(np.ndarray.any(np.asarray(self)))
 
 
 def _mask(a):
@@ -264,6 +264,36 @@ class Ensemble:
         check(self._L.ni_ensemble_ff2cond(self._h, int(kind), int(index), float(value), hit.ctypes.data, n_hit))
         return bool(hit[0]) if self._single else _mask(hit)
 
+    # ------------------------------------------------------------------ bulk host<->device paths
+    def set_stream(self, cuda_stream):
+        """Launch on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._L.ni_ensemble_set_stream(self._h, _lib._vp(int(cuda_stream))))
+
+    def upload(self, t0, y0, parameters, t_bound):
+        """Asynchronous host -> HBM copy of new inputs: y0 (N, n), parameters (N, P) row-major float64
+        buffers (numpy arrays or pinned torch tensors), t0 / t_bound scalars or (N,) buffers."""
+        t0p, t0n = _buf(t0, self.N)
+        tbp, tbn = _buf(t_bound, self.N)
+        self._keep = (t0p, tbp)  # scalars live in small arrays until the copy has been issued
+        check(self._L.ni_ensemble_upload(self._h, _ptr(t0p), int(t0n), _ptr(y0), _ptr(parameters) if self.P else None,
+                                         _ptr(tbp), int(tbn)))
+
+    def reset(self):
+        """Re-run the constructor math (FSAL seed, select_initial_step) on the resident inputs (async)."""
+        check(self._L.ni_ensemble_reset(self._h, self.rtol.ctypes.data_as(_lib._dp),
+                                        self.atol.ctypes.data_as(_lib._dp), self.max_step, self._first_step))
+
+    def run_async(self):
+        check(self._L.ni_ensemble_run_async(self._h))
+
+    def sync(self):
+        check(self._L.ni_ensemble_sync(self._h))
+
+    def fetch(self, field, out):
+        """Device -> host copy of one field into a caller-owned buffer (numpy array / pinned tensor)."""
+        check(self._L.ni_ensemble_get(self._h, int(field), _ptr(out)))
+        return out
+
     # ------------------------------------------------------------------ recording
     def record_enable(self, capacity):
         check(self._L.ni_ensemble_record_enable(self._h, int(capacity)))
@@ -294,6 +324,24 @@ class Ensemble:
         a, b, c = C.c_float(0), C.c_float(0), C.c_int64(0)
         check(self._L.ni_ensemble_timing(self._h, a, b, c))
         return dict(ms_init=a.value, ms_run=b.value, launches=c.value)
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if hasattr(x, 'data_ptr'):  # torch tensor (e.g. pinned host memory)
+        return _lib._vp(x.data_ptr())
+    return _lib._vp(np.ascontiguousarray(x).ctypes.data) if not isinstance(x, np.ndarray) else _lib._vp(x.ctypes.data)
+
+
+def _buf(v, N):
+    """(buffer, per_trajectory) for a scalar or an (N,) float64 buffer."""
+    if hasattr(v, 'data_ptr'):
+        return v, v.numel() > 1
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+    if a.size not in (1, N):
+        raise ValueError(f'expected a scalar or {N} values, got {a.size}')
+    return a, a.size > 1 or N == 1
 
 
 def _flatten_parameters(parameters):

@@ -1,0 +1,168 @@
+"""Reference API behaviour on the GPU path; each test mirrors one in the reference's
+tests/unittests/test_public.py (line numbers cited)."""
+import numpy as np
+import pytest
+
+import numba_integrators_b200 as ni
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_example():  # README.md:47-69
+    solver = ni.RK45(ni.rhs.harmonic, 0.0, np.array((0., 1.)), t_bound=1, atol=1e-8, rtol=1e-8)
+    t, y = [], []
+    while ni.step(solver):
+        t.append(solver.t)
+        y.append(solver.y)
+    meta, g = load_golden('c1_readme_sine_rk45')
+    assert len(t) == 11 and t[-1] == 1.0
+    assert np.allclose(t, g['rec_t'][0], rtol=1e-12) and np.allclose(np.array(y), g['rec_y'][0], rtol=1e-12)
+    assert isinstance(solver.t, float) and solver.y.shape == (2,)
+    assert y[0] is not y[1]                                    # solver.y is a fresh array after every step
+
+
+def test_readme_advanced_example():  # README.md:74-111
+    Solver = ni.Advanced(3, 1, ni.RK45)
+    solver = Solver(ni.rhs.readme_advanced, 0., np.array((0., 1.)), (2., np.array((-1., 1.))), t_bound=1, atol=1e-8,
+                    rtol=1e-8)
+    meta, g = load_golden('readme_advanced_rk45')
+    assert np.allclose(solver.auxiliary, g['aux0'][0])
+    k = 0
+    while ni.step(solver):
+        assert abs(solver.t - g['rec_t'][0, k]) < 1e-12
+        k += 1
+    assert k == g['n_accepted'][0] and np.allclose(solver.auxiliary, g['aux'][0], rtol=1e-12)
+    t, y, aux = solver.state
+    assert t == 1.0
+
+
+@pytest.mark.parametrize('method', ['RK23', 'RK45'])
+@pytest.mark.parametrize('problem', ['riccati', 'sine', 'exponential'])
+def test_to_reference_problems(method, problem):  # test_public.py:17-46 (rtol = atol = 1e-10)
+    meta, g = load_golden(f'problem_{problem}_{method.lower()}')
+    ctor = ni.RK45 if method == 'RK45' else ni.RK23
+    solver = ctor(ni.BuiltinRHS(meta['rhs']), g['t0'][0], g['y0'][0], g['t_bound'][0], rtol=1e-10, atol=1e-10)
+    while ni.step(solver):
+        pass
+    assert solver.t == g['t_bound'][0]                         # :26
+    assert solver.n_accepted == g['n_accepted'][0] and solver.n_rejected == g['n_rejected'][0]
+    assert np.allclose(solver.y, g['y'][0], rtol=1e-12, atol=0)
+
+
+def test_max_step():  # test_public.py:48-61
+    max_step = 1e-4
+    low = max_step * (1 - 1e-13)
+    solver = ni.RK45(ni.rhs.exponential, 0.0, np.array((1.,)), t_bound=10.0, first_step=max_step, max_step=max_step)
+    meta, g = load_golden('max_step_exponential')
+    x_prev = solver.t
+    for k in range(100):
+        ni.step(solver)
+        assert low < (solver.t - x_prev) <= max_step
+        assert solver.t == g['rec_t'][0, k]
+        x_prev = solver.t
+    solver = ni.RK45(ni.rhs.exponential, 0.0, np.array((1.,)), t_bound=10.0, max_step=max_step)   # :127-142
+    x_prev = solver.t
+    for _ in range(100):
+        ni.step(solver)
+        assert low < (solver.t - x_prev) <= max_step
+        x_prev = solver.t
+
+
+@pytest.mark.parametrize('method', [ni.RK23, ni.RK45])
+def test_advanced_identical_to_base(method):  # test_public.py:79-125: bitwise identical t and y at every step
+    base = method(ni.rhs.exponential, 0.0, np.array((1.,)), 10.0)
+    adv = ni.Advanced(0, 0, method)(ni.rhs.exponential, 0.0, np.array((1.,)), None, 10.0)
+    assert base.t == adv.t and np.all(base.y == adv.y)
+    while ni.step(base):
+        assert ni.step(adv)
+        assert base.t == adv.t and np.all(base.y == adv.y)
+    assert not ni.step(adv)
+
+
+def test_ff2t():  # test_public.py:150-165
+    solver = ni.RK45(ni.rhs.exponential, 0.0, np.array((1.,)), 10.0)
+    t_step1 = 10.0 / 10.1
+    assert ni.ff2t(solver, t_step1) is True
+    assert solver.t == t_step1
+    assert solver.t_bound == 10.0
+    while ni.ff2t(solver, solver.t + t_step1):
+        ...
+    assert solver.t == solver.t_bound == 10.0
+
+
+def test_ff2cond():  # test_public.py:167-175, once with a host predicate and once with the device predicate
+    def condition(solver, parameters):
+        return solver.y[0] > parameters
+    a = ni.RK45(ni.rhs.exponential, 0.0, np.array((1.,)), 10.0)
+    assert ni.ff2cond(a, condition, 4.)
+    assert condition(a, 4.)
+    b = ni.RK45(ni.rhs.exponential, 0.0, np.array((1.,)), 10.0)
+    assert ni.ff2cond(b, ni.y_above(0), 4.)
+    assert b.t == a.t and np.all(b.y == a.y)
+    c = ni.RK45(ni.rhs.exponential, 0.0, np.array((1.,)), 1.0)
+    assert not ni.ff2cond(c, ni.y_above(0), 4.)               # reaches t_bound first
+    assert c.t == 1.0
+
+
+def test_failure_exit_commits_rejected_state():  # _basic.py:179-180, SURVEY A.2-10
+    meta, g = load_golden('failure_blowup_rk45_basic')
+    solver = ni.RK45(ni.rhs.blowup, 0.0, np.array((1.,)), 2.0, rtol=1e-8, atol=1e-8)
+    k = 0
+    while ni.step(solver):
+        k += 1
+    assert k == 499 and solver.status == 2
+    assert abs(solver.t - g['t'][0]) < 1e-12 and solver.t != 2.0
+    assert not ni.step(solver)                                 # latched
+
+
+def test_ensemble_semantics_and_records():
+    rng = np.random.default_rng(0)
+    y0 = rng.uniform(-1, 1, size=(1000, 2))
+    ens = ni.RK45(ni.rhs.harmonic, 0.0, y0, 3.0, rtol=1e-8, atol=1e-8, record=100_000)
+    steps = 0
+    while ni.step(ens):                                        # mask with any() truthiness
+        steps += 1
+    assert np.all(ens.t == 3.0) and steps == ens.n_accepted.max()
+    rec = ens.record_drain().sorted()
+    assert len(rec) == ens.n_accepted.sum()
+    t5, y5, _ = rec.trajectory(5)
+    single = ni.RK45(ni.rhs.harmonic, 0.0, y0[5], 3.0, rtol=1e-8, atol=1e-8)
+    ts = []
+    while ni.step(single):
+        ts.append(single.t)
+    assert np.array_equal(t5, np.array(ts)) and np.array_equal(y5[-1], single.y)
+    # fast-forward with recording and a log that is too small: drain and continue
+    ens2 = ni.RK45(ni.rhs.harmonic, 0.0, y0, 3.0, rtol=1e-8, atol=1e-8, record=5000)
+    got = 0
+    for _ in range(100):
+        try:
+            ens2.run()
+            got += len(ens2.record_drain())
+            break
+        except ni.NiError as e:
+            assert e.code == -6
+            got += len(ens2.record_drain())
+    assert got == ens.n_accepted.sum()
+    assert np.array_equal(ens2.y, ens.y) and np.array_equal(ens2.n_accepted, ens.n_accepted)
+
+
+def test_user_rhs_snippet_matches_builtin():
+    body = '''
+        dy[0] = __dmul_rn(p[0], __dadd_rn(y[1], -y[0]));
+        dy[1] = __dadd_rn(__dmul_rn(y[0], __dadd_rn(p[1], -y[2])), -y[1]);
+        dy[2] = __dadd_rn(__dmul_rn(y[0], y[1]), -__dmul_rn(p[2], y[2]));
+        aux[0] = __dadd_rn(__dadd_rn(__dmul_rn(y[0], y[0]), __dmul_rn(y[1], y[1])), __dmul_rn(y[2], y[2]));
+    '''
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c3_lorenz(N=512, t_bound=1.0)
+    user = ni.CudaRHS(body, n=3, P=3, Q=1, name='lorenz_user')
+    a = ni.Advanced(3, 1, ni.RK45)(user, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    b = ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    a.run()
+    b.run()
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.auxiliary, b.auxiliary)
+    assert np.array_equal(a.n_accepted, b.n_accepted) and np.array_equal(a.n_rejected, b.n_rejected)
+    with pytest.raises(ni.NiError) as ei:
+        ni.RK45(ni.CudaRHS('dy[0] = undefined_symbol;', n=1), 0.0, np.ones(1), 1.0)
+    assert ei.value.code == -3
