@@ -24,7 +24,7 @@
 #define NI_API extern "C" __attribute__((visibility("default")))
 
 extern const char ni_core_source[];   // ni_core.cuh as a string (generated: ni_core_src.cpp)
-extern const char ni_large_source[];  // ni_large.cuh as a string
+extern const char ni_math_source[];   // ni_math.cuh as a string
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -190,9 +190,9 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
          "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true>(a); }\n";
 
   nvrtcProgram prog = nullptr;
-  const char *hdr_src[] = {ni_core_source};
-  const char *hdr_name[] = {"ni_core.cuh"};
-  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 1, hdr_src, hdr_name);
+  const char *hdr_src[] = {ni_core_source, ni_math_source};
+  const char *hdr_name[] = {"ni_core.cuh", "ni_math.cuh"};
+  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 2, hdr_src, hdr_name);
   if (rc) return fail(NI_ERR_NVRTC, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(rc));
   std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
                                    "-default-device"};

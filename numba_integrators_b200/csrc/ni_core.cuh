@@ -42,6 +42,8 @@
 #define NI_DEV __device__ __forceinline__
 #define NI_HD __host__ __device__
 
+#include "ni_math.cuh"
+
 // Kernel arguments (passed by value).  All per-trajectory arrays have N entries;
 // y, klast are [n][N], params [P][N], aux [Q][N].
 struct NiArgs {
@@ -161,6 +163,32 @@ struct NiTab<NI_RK45> {
   }
 };
 
+// The same coefficients in constant memory: FP64 instructions take them as c[bank][offset] operands,
+// which saves the two UMOVs per use that 64-bit immediates cost.  Index: row*8 + column, rows as in
+// ni_coef (1..S-1 = A, S = B, S+1 = E), row 0 = C.
+#define NI_TAB_ROW(T, r) T(r, 0), T(r, 1), T(r, 2), T(r, 3), T(r, 4), T(r, 5), T(r, 6), T(r, 7)
+NI_HD constexpr double ni_tab23(int r, int j) {
+  using T = NiTab<NI_RK23>;
+  return r == 0 ? T::c(j) : r < T::S ? T::a(r, j) : r == T::S ? T::b(j) : r == T::S + 1 ? T::e(j) : 0.0;
+}
+NI_HD constexpr double ni_tab45(int r, int j) {
+  using T = NiTab<NI_RK45>;
+  return r == 0 ? T::c(j) : r < T::S ? T::a(r, j) : r == T::S ? T::b(j) : r == T::S + 1 ? T::e(j) : 0.0;
+}
+__constant__ double ni_ctab23[5 * 8] = {NI_TAB_ROW(ni_tab23, 0), NI_TAB_ROW(ni_tab23, 1), NI_TAB_ROW(ni_tab23, 2),
+                                        NI_TAB_ROW(ni_tab23, 3), NI_TAB_ROW(ni_tab23, 4)};
+__constant__ double ni_ctab45[8 * 8] = {NI_TAB_ROW(ni_tab45, 0), NI_TAB_ROW(ni_tab45, 1), NI_TAB_ROW(ni_tab45, 2),
+                                        NI_TAB_ROW(ni_tab45, 3), NI_TAB_ROW(ni_tab45, 4), NI_TAB_ROW(ni_tab45, 5),
+                                        NI_TAB_ROW(ni_tab45, 6), NI_TAB_ROW(ni_tab45, 7)};
+// run-time value of coefficient (ROW, J); ROW = 0 gives C[J]
+template <int METHOD, int ROW, int J>
+NI_DEV double ni_cval() {
+  if constexpr (METHOD == NI_RK45)
+    return ni_ctab45[ROW * 8 + J];
+  else
+    return ni_ctab23[ROW * 8 + J];
+}
+
 // Coefficient of row ROW, column j.  ROW in 1..S-1 -> A[ROW][j]; ROW == S -> B[j]; ROW == S+1 -> E[j].
 template <int METHOD, int ROW>
 NI_HD constexpr double ni_coef(int j) {
@@ -176,7 +204,7 @@ NI_DEV double ni_fma_term(double x, double acc) {
   if constexpr (c == 0.0)
     return acc;
   else
-    return fma(x, c, acc);
+    return fma(x, ni_cval<METHOD, ROW, J>(), acc);
 }
 // fma(xi, ci, rn(xj*cj)): the seed pair of the dgemv order
 template <int METHOD, int ROW, int I, int J>
@@ -185,11 +213,11 @@ NI_DEV double ni_pair(double xi, double xj) {
   if constexpr (ci == 0.0 && cj == 0.0)
     return 0.0;
   else if constexpr (cj == 0.0)
-    return __dmul_rn(xi, ci);
+    return __dmul_rn(xi, ni_cval<METHOD, ROW, I>());
   else if constexpr (ci == 0.0)
-    return __dmul_rn(xj, cj);
+    return __dmul_rn(xj, ni_cval<METHOD, ROW, J>());
   else
-    return fma(xi, ci, __dmul_rn(xj, cj));
+    return fma(xi, ni_cval<METHOD, ROW, I>(), __dmul_rn(xj, ni_cval<METHOD, ROW, J>()));
 }
 
 // out[i] = sum_{j<COLS} K[j][i] * coef(j) in the order OpenBLAS dgemv_n uses for an (n x COLS)
@@ -206,13 +234,14 @@ NI_DEV void ni_dot(const double (&K)[KR][n], double (&out)[n]) {
         constexpr int j = decltype(jj)::value;
         constexpr double c = ni_coef<METHOD, ROW>(j);
         if constexpr (c != 0.0) {
-          acc = first ? __dmul_rn(K[j][i], c) : fma(K[j][i], c, acc);
+          const double cv = ni_cval<METHOD, ROW, j>();
+          acc = first ? __dmul_rn(K[j][i], cv) : fma(K[j][i], cv, acc);
           first = false;
         }
       });
     } else {
       if constexpr (n == 1) {
-        acc = __dmul_rn(K[1][i], ni_coef<METHOD, ROW>(1));
+        acc = __dmul_rn(K[1][i], ni_cval<METHOD, ROW, 1>());
         acc = ni_fma_term<METHOD, ROW, 0>(K[0][i], acc);
         acc = ni_fma_term<METHOD, ROW, 2>(K[2][i], acc);
         acc = ni_fma_term<METHOD, ROW, 3>(K[3][i], acc);
@@ -234,7 +263,10 @@ NI_DEV double ni_rms(const double (&x)[n]) {
   double acc = __dmul_rn(x[0], x[0]);
 #pragma unroll
   for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(x[i], x[i]));
-  return sqrt(acc / (double)n);
+  if constexpr (n == 3)
+    return sqrt(ni_div3(acc));
+  else
+    return sqrt(acc / (double)n);
 }
 
 NI_DEV double ni_pow(double x, double e) { return pow(x, e); }
@@ -354,7 +386,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   const unsigned lane = threadIdx.x & 31u;
 
   long long idx = 0;
-  bool active = false, exhausted = false, fresh = true, last_accept = false;
+  bool active = false, exhausted = false, fresh = true, last_accept = false, parked = false;
   double t = 0, h_abs = 0, tb = 0, dir = 1, eps = 0, min_step = 0, step_h = 0;
   double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
   int nacc = 0, nrej = 0, status = NI_ST_RUNNING;
@@ -375,7 +407,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     a.n_acc[idx] = nacc;
     a.n_rej[idx] = nrej;
     a.running[idx] = last_accept ? 1 : 0;
-    if (status == NI_ST_RUNNING) atomicAdd(a.queue + 2, 1ull);
+    if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
     if (last_accept) atomicAdd(a.queue + 3, 1ull);
     active = false;
   };
@@ -393,6 +425,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         exhausted = true;
       } else {
         status = a.status[idx];
+        if (a.cond_kind != 0 && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
         if (status == NI_ST_RUNNING) {
           t = a.t[idx];
           h_abs = a.h_abs[idx];
@@ -414,8 +447,9 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           acc_left = a.max_accepts;
           fresh = true;
           last_accept = false;
+          parked = false;
           active = true;
-        } else {
+        } else if (status >= 0) {
           a.running[idx] = 0;  // step() on a finished / failed solver returns False
         }
       }
@@ -440,40 +474,41 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     // ---- one attempt (_basic.py:145-169)
     bool ok = false;
     double tn = 0, h = 0, h_pre = 0, en = 0;
-    double K[S + 1][n], yn[n], auxn[Q > 0 ? Q : 1];
+    double kn[n], yn[n], auxn[Q > 0 ? Q : 1];
     if (active) {
       h_pre = h_abs;
       if (h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
       h = ADV ? __dmul_rn(h_abs, dir) : h_abs;
       tn = __dadd_rn(t, h);
-#pragma unroll
-      for (int i = 0; i < n; ++i) K[0][i] = kl[i];  // K[0] = K[-1]: stale after a rejection
       if (__dmul_rn(dir, __dadd_rn(tn, -tb)) >= 0.0) {
         tn = tb;
         h = __dadd_rn(tn, -t);
         h_abs = fabs(h);
       }
+      double K[S + 1][n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) K[0][i] = kl[i];  // K[0] = K[-1]: stale after a rejection (:151)
       ni_static_for<1, S>([&](auto ss) {
         constexpr int s = decltype(ss)::value;
         double d[n], ys[n], auxd[Q > 0 ? Q : 1];
         ni_dot<METHOD, s, s, n>(K, d);
 #pragma unroll
         for (int i = 0; i < n; ++i) ys[i] = __dadd_rn(y[i], __dmul_rn(d[i], h));
-        Rhs::eval(__dadd_rn(t, __dmul_rn(Tab::c(s), h)), ys, p, K[s], auxd);
+        Rhs::eval(__dadd_rn(t, __dmul_rn(ni_cval<METHOD, 0, s>(), h)), ys, p, K[s], auxd);
       });
-      {
-        double d[n];
-        ni_dot<METHOD, S, S, n>(K, d);
+      double d[n];
+      ni_dot<METHOD, S, S, n>(K, d);
 #pragma unroll
-        for (int i = 0; i < n; ++i) yn[i] = __dadd_rn(y[i], __dmul_rn(h, d[i]));
-        Rhs::eval(tn, yn, p, K[S], auxn);
-        double ev[n];
-        ni_dot<METHOD, S + 1, S + 1, n>(K, ev);
+      for (int i = 0; i < n; ++i) yn[i] = __dadd_rn(y[i], __dmul_rn(h, d[i]));
+      Rhs::eval(tn, yn, p, K[S], auxn);
+      double ev[n];
+      ni_dot<METHOD, S + 1, S + 1, n>(K, ev);
 #pragma unroll
-        for (int i = 0; i < n; ++i)
-          ev[i] = __dmul_rn(ev[i], h) / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
-        en = ni_rms<n>(ev);
+      for (int i = 0; i < n; ++i) {
+        ev[i] = __dmul_rn(ev[i], h) / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+        kn[i] = K[S][i];
       }
+      en = ni_rms<n>(ev);
       ok = en < 1.0;
       --att_left;
     }
@@ -491,84 +526,63 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       }
     }
 
-    // ---- controller + commit (_basic.py:171-180)
+    // ---- controller + commit (_basic.py:171-180), branch-free for the accept / reject split so that a
+    // warp with both kinds of lanes runs the controller once
     if (active) {
-      if (ok) {
-        if (REC && slot >= a.rec_cap) {
-          // log full: undo this attempt and park the trajectory (restartable: the state before
-          // an attempt is exactly t, y, h_abs, K[-1])
-          atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
-          h_abs = h_pre;
-          ++att_left;
-          last_accept = false;
-          retire();
-        } else {
-          const double fac = (en == 0.0) ? 10.0 : fmin(10.0, __dmul_rn(0.9, ni_pow(en, err_exp)));
-          h_abs = __dmul_rn(h_abs, fac);
-          t = tn;
-          step_h = h;
+      const bool nan = !ok && !(en >= 1.0);
+      const bool park = REC && ok && slot >= a.rec_cap;  // log full: undo this attempt (state before an
+                                                         // attempt is exactly t, y, h_abs, K[-1])
+      // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
+      const double sp = __dmul_rn(0.9, ni_pow_ctrl<Tab::ORDER + 1>(en));
+      const double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      const double h_new = __dmul_rn(h_abs, fac);
+      const bool fail = !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
+      const bool take = (ok && !park) || fail;
+      h_abs = park ? h_pre : (nan ? h_abs : h_new);
+      t = take ? tn : t;
+      step_h = (take || nan) ? h : step_h;
 #pragma unroll
-          for (int i = 0; i < n; ++i) {
-            y[i] = yn[i];
-            kl[i] = K[S][i];
-          }
-#pragma unroll
-          for (int i = 0; i < Q; ++i) aux[i] = auxn[i];
-          ++nacc;
-          --acc_left;
-          fresh = true;
-          last_accept = true;
-          if (REC) {
-            const long long c = a.rec_cap;
-            a.rec_traj[slot] = (unsigned int)idx;
-            a.rec_step[slot] = (unsigned int)nacc;
-            a.rec_t[slot] = t;
-#pragma unroll
-            for (int i = 0; i < n; ++i) a.rec_y[i * c + slot] = y[i];
-#pragma unroll
-            for (int i = 0; i < Q; ++i) a.rec_aux[i * c + slot] = aux[i];
-          }
-          bool hit = false;
-          if (a.cond_kind != 0) {
-            hit = ni_cond_test<n, Q>(a, y, aux);
-            if (hit) a.cond_hit[idx] = 1;
-          }
-          if (hit || acc_left <= 0 || att_left <= 0) {
-            retire();
-          } else if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
-            // fast-forward: the terminal step() call of `while step(): pass`
-            step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
-            status = NI_ST_FINISHED;
-            last_accept = false;
-            retire();
-          }
-        }
-      } else if (!(en >= 1.0)) {
-        ++nrej;
-        status = NI_ST_NONFINITE;
-        step_h = h;
-        last_accept = false;
-        retire();
-      } else {
-        const double fac = fmax(0.2, __dmul_rn(0.9, ni_pow(en, err_exp)));
-        h_abs = __dmul_rn(h_abs, fac);
-        ++nrej;
-#pragma unroll
-        for (int i = 0; i < n; ++i) kl[i] = K[S][i];
-        last_accept = false;
-        if (h_abs < min_step) {  // too small a step: the reference commits the REJECTED t, y
-          t = tn;
-          step_h = h;
-#pragma unroll
-          for (int i = 0; i < n; ++i) y[i] = yn[i];
-#pragma unroll
-          for (int i = 0; i < Q; ++i) aux[i] = auxn[i];
-          status = NI_ST_FAILED;
-          retire();
-        } else if (att_left <= 0) {
-          retire();
-        }
+      for (int i = 0; i < n; ++i) {
+        y[i] = take ? yn[i] : y[i];
+        kl[i] = park ? kl[i] : kn[i];
       }
+#pragma unroll
+      for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
+      const bool accepted = ok && !park;
+      nacc += accepted ? 1 : 0;
+      nrej += (ok || park) ? 0 : 1;
+      acc_left -= accepted ? 1 : 0;
+      att_left += park ? 1 : 0;
+      fresh = accepted;
+      last_accept = accepted;
+      if (REC && accepted) {
+        const long long c = a.rec_cap;
+        a.rec_traj[slot] = (unsigned int)idx;
+        a.rec_step[slot] = (unsigned int)nacc;
+        a.rec_t[slot] = t;
+#pragma unroll
+        for (int i = 0; i < n; ++i) a.rec_y[i * c + slot] = y[i];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) a.rec_aux[i * c + slot] = aux[i];
+      }
+      // ---- rare exits
+      bool done = park || fail || nan || att_left <= 0 || (accepted && acc_left <= 0);
+      if (park) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+      if (fail) status = NI_ST_FAILED;
+      if (nan) status = NI_ST_NONFINITE;
+      if (accepted && a.cond_kind != 0 && ni_cond_test<n, Q>(a, y, aux)) {
+        a.cond_hit[idx] = 1;
+        parked = true;
+        done = true;
+      }
+      if (accepted && !done && __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
+        // fast-forward: the terminal step() call of `while step(): pass` (_basic.py:135-136)
+        step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
+        status = NI_ST_FINISHED;
+        last_accept = false;
+        done = true;
+      }
+      if (done) retire();
     }
   }
 }

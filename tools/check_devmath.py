@@ -1,0 +1,76 @@
+"""Host-side check of the device controller math in csrc/ni_math.cuh (compiled as plain C++):
+
+  * ni_pow_ctrl<5>/<3> against the correctly rounded x**e (decimal, 60 digits) and against glibc pow
+    (what the reference's numba code calls) on random error norms;
+  * ni_div3 against IEEE division.
+
+    python tools/check_devmath.py [n_samples]
+"""
+import ctypes
+import subprocess
+import sys
+import tempfile
+from decimal import Decimal, getcontext
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = r'''
+#define NI_MATH_HOST
+#include "ni_math.cuh"
+extern "C" {
+double pow5(double x) { return ni_pow_ctrl<5>(x); }
+double pow3(double x) { return ni_pow_ctrl<3>(x); }
+double div3(double x) { return ni_div3(x); }
+double libm_pow(double x, double e) { return std::pow(x, e); }
+void div3_check(const double* a, long n, long* bad) { long b = 0; for (long i = 0; i < n; ++i) b += (ni_div3(a[i]) != a[i] / 3.0); *bad = b; }
+}
+'''
+
+
+def build():
+    d = Path(tempfile.mkdtemp(prefix='ni_devmath_'))
+    (d / 't.cpp').write_text(SRC)
+    so = d / 'libt.so'
+    subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-mfma', '-shared', '-fPIC', '-I',
+                    str(ROOT / 'numba_integrators_b200' / 'csrc'), str(d / 't.cpp'), '-o', str(so)], check=True)
+    L = ctypes.CDLL(str(so))
+    for f in ('pow5', 'pow3', 'div3'):
+        getattr(L, f).restype = ctypes.c_double
+        getattr(L, f).argtypes = [ctypes.c_double]
+    L.libm_pow.restype = ctypes.c_double
+    L.libm_pow.argtypes = [ctypes.c_double, ctypes.c_double]
+    return L
+
+
+def main(n=20000):
+    L = build()
+    getcontext().prec = 60
+    rng = np.random.default_rng(0)
+    res = {}
+    for name, f, e in (('RK45 e=-0.2', L.pow5, -0.2), ('RK23 e=RN(-1/3)', L.pow3, -1 / 3)):
+        De = Decimal(e)
+        # error norms as the controller sees them: log-uniform over 1e-6..1e3 plus a wide tail
+        xs = np.concatenate([10.0 ** rng.uniform(-6, 3, n), 10.0 ** rng.uniform(-29, 29, n // 4)])
+        bad_mine = bad_libm = differ = 0
+        for x in xs:
+            x = float(x)
+            cr = float(Decimal(x) ** De)
+            mine, lm = f(x), L.libm_pow(x, e)
+            bad_mine += mine != cr
+            bad_libm += lm != cr
+            differ += mine != lm
+        res[name] = (bad_mine, bad_libm, differ, len(xs))
+        print(f'{name:18s} samples={len(xs)}  ni_pow_ctrl != CR: {bad_mine}   glibc pow != CR: {bad_libm}   '
+              f'ni_pow_ctrl != glibc: {differ}')
+    a = np.concatenate([rng.uniform(0, 10, 2_000_000), 10.0 ** rng.uniform(-300, 300, 2_000_000)])
+    bad = ctypes.c_long(0)
+    L.div3_check(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(a), ctypes.byref(bad))
+    print(f'ni_div3 != a/3.0 on {bad.value} of {len(a)} samples')
+    res['div3'] = bad.value
+    return res
+
+
+if __name__ == '__main__':
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 20000)
