@@ -385,7 +385,17 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
   NI_TRY(dalloc(e, &e->params_rows, sN * P))
   NI_TRY(dalloc(e, &e->tb_saved, sN))
   NI_TRY(dalloc(e, &e->flag_d, sN))
-  if (rc == NI_OK && m->kind == NI_KIND_LARGE) rc = ni_large_prepare(&e->mod.large, &a, n, device, e->sms) ? NI_OK : fail(NI_ERR_CUDA, "large-kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc == NI_OK && m->kind == NI_KIND_LARGE) {
+    rc = dalloc(e, &e->mod.large.tol_d, 2 * (size_t)n);
+    a.n = n;
+    a.rtol_d = e->mod.large.tol_d;
+    a.atol_d = e->mod.large.tol_d + n;
+    for (const void *k : {m->k_init, m->k_run[0], m->k_run[1]}) {  // opt in to > 48 KB of dynamic shared memory
+      cudaError_t ce2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem);
+      if (rc == NI_OK && ce2 != cudaSuccess)
+        rc = fail(NI_ERR_CUDA, "cudaFuncSetAttribute(%zu B shared memory): %s", m->smem, cudaGetErrorString(ce2));
+    }
+  }
 #undef NI_TRY
   if (rc != NI_OK) {
     std::string keep = g_err;
@@ -475,7 +485,9 @@ NI_API int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *a
       e->a.atol[i] = atol[i];
     }
   } else {
-    if (int rc = ni_large_set_tolerances(&e->mod.large, &e->a, rtol, atol, n, e->stream)) return fail(NI_ERR_CUDA, "tolerance upload failed (%d)", rc);
+    CU(cudaMemcpyAsync(e->mod.large.tol_d, rtol, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->mod.large.tol_d + n, atol, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));  // rtol / atol are caller-owned host buffers
   }
   e->a.max_step = max_step;
   e->a.first_step = first_step;

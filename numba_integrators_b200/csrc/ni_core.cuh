@@ -59,6 +59,8 @@ struct NiArgs {
   const double *params_rows;    // init only: N x P row-major
   double max_step, first_step;
   double rtol[NI_MAX_SMALL_N], atol[NI_MAX_SMALL_N];
+  int n;                        // large kernels: state dimension (run-time)
+  const double *rtol_d, *atol_d;  // large kernels: tolerance vectors in HBM (n entries)
   unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted
   long long max_attempts;       // per trajectory per launch (bounds kernel time)
   long long max_accepts;        // 1 = lock-step ni.step(), huge = fast-forward
@@ -196,65 +198,73 @@ NI_HD constexpr double ni_coef(int j) {
   return ROW < T::S ? T::a(ROW, j) : ROW == T::S ? T::b(j) : T::e(j);
 }
 
-// fma(x, c, acc) with the structural zeros of the tableau skipped (fma(x, 0, acc) == acc for
-// finite x; the reference does not skip them, the results differ only for non-finite x).
-template <int METHOD, int ROW, int J>
-NI_DEV double ni_fma_term(double x, double acc) {
-  constexpr double c = ni_coef<METHOD, ROW>(J);
-  if constexpr (c == 0.0)
-    return acc;
-  else
-    return fma(x, ni_cval<METHOD, ROW, J>(), acc);
-}
-// fma(xi, ci, rn(xj*cj)): the seed pair of the dgemv order
-template <int METHOD, int ROW, int I, int J>
-NI_DEV double ni_pair(double xi, double xj) {
-  constexpr double ci = ni_coef<METHOD, ROW>(I), cj = ni_coef<METHOD, ROW>(J);
-  if constexpr (ci == 0.0 && cj == 0.0)
-    return 0.0;
-  else if constexpr (cj == 0.0)
-    return __dmul_rn(xi, ni_cval<METHOD, ROW, I>());
-  else if constexpr (ci == 0.0)
-    return __dmul_rn(xj, ni_cval<METHOD, ROW, J>());
-  else
-    return fma(xi, ni_cval<METHOD, ROW, I>(), __dmul_rn(xj, ni_cval<METHOD, ROW, J>()));
+// sum_{j<COLS} K_j * coef(ROW, j) for ONE component, in the order OpenBLAS dgemv_n uses for an
+// (n x COLS) matrix with n <= 3 rows (oracle/ni_oracle.c:dot_cols is the CPU
+// twin): COLS <= 3 is a plain FMA chain; otherwise fma(K0,c0,K1*c1) + fma(K2,c2,K3*c3) (n >= 2) or
+// the chain seeded with K1*c1 (n == 1, ONE_ROW), followed by the FMA tail j = 4...  `k(NiInt<j>{})`
+// returns K_j and is only called for non-zero coefficients: fma(x, 0, acc) == acc for finite x, so
+// the structural zeros of the tableau are skipped (the reference does not skip them; results differ
+// only for non-finite K).
+template <int METHOD, int ROW, int COLS, bool ONE_ROW, class G>
+NI_DEV double ni_dot_col(G &&k) {
+  double acc = 0.0;
+  auto term = [&](auto jj, double acc_in, bool have) -> double {
+    constexpr int j = decltype(jj)::value;
+    const double cv = ni_cval<METHOD, ROW, j>();
+    return have ? fma(k(jj), cv, acc_in) : __dmul_rn(k(jj), cv);
+  };
+  if constexpr (COLS <= 3) {
+    bool have = false;
+    ni_static_for<0, COLS>([&](auto jj) {
+      if constexpr (ni_coef<METHOD, ROW>(decltype(jj)::value) != 0.0) {
+        acc = term(jj, acc, have);
+        have = true;
+      }
+    });
+  } else if constexpr (ONE_ROW) {
+    bool have = false;
+    if constexpr (ni_coef<METHOD, ROW>(1) != 0.0) {
+      acc = term(NiInt<1>{}, acc, false);
+      have = true;
+    }
+    if constexpr (ni_coef<METHOD, ROW>(0) != 0.0) {
+      acc = term(NiInt<0>{}, acc, have);
+      have = true;
+    }
+    if constexpr (ni_coef<METHOD, ROW>(2) != 0.0) {
+      acc = term(NiInt<2>{}, acc, have);
+      have = true;
+    }
+    if constexpr (ni_coef<METHOD, ROW>(3) != 0.0) acc = term(NiInt<3>{}, acc, have);
+  } else {
+    auto pair = [&](auto ii, auto jj) -> double {  // fma(K_i, c_i, rn(K_j * c_j))
+      constexpr int i = decltype(ii)::value, j = decltype(jj)::value;
+      constexpr double ci = ni_coef<METHOD, ROW>(i), cj = ni_coef<METHOD, ROW>(j);
+      if constexpr (ci == 0.0 && cj == 0.0)
+        return 0.0;
+      else if constexpr (cj == 0.0)
+        return __dmul_rn(k(ii), ni_cval<METHOD, ROW, i>());
+      else if constexpr (ci == 0.0)
+        return __dmul_rn(k(jj), ni_cval<METHOD, ROW, j>());
+      else
+        return fma(k(ii), ni_cval<METHOD, ROW, i>(), __dmul_rn(k(jj), ni_cval<METHOD, ROW, j>()));
+    };
+    acc = __dadd_rn(pair(NiInt<0>{}, NiInt<1>{}), pair(NiInt<2>{}, NiInt<3>{}));
+  }
+  if constexpr (COLS > 4) {
+    ni_static_for<4, COLS>([&](auto jj) {
+      if constexpr (ni_coef<METHOD, ROW>(decltype(jj)::value) != 0.0) acc = term(jj, acc, true);
+    });
+  }
+  return acc;
 }
 
-// out[i] = sum_{j<COLS} K[j][i] * coef(j) in the order OpenBLAS dgemv_n uses for an (n x COLS)
-// matrix with n <= 3 rows (oracle/ni_oracle.c:dot_cols is the CPU twin).
+// out[i] = sum_{j<COLS} K[j][i] * coef(j) for the register-resident stage matrix of the small kernels
 template <int METHOD, int ROW, int COLS, int n, int KR>
 NI_DEV void ni_dot(const double (&K)[KR][n], double (&out)[n]) {
 #pragma unroll
-  for (int i = 0; i < n; ++i) {
-    double acc;
-    if constexpr (COLS <= 3) {
-      acc = 0.0;
-      bool first = true;
-      ni_static_for<0, COLS>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        constexpr double c = ni_coef<METHOD, ROW>(j);
-        if constexpr (c != 0.0) {
-          const double cv = ni_cval<METHOD, ROW, j>();
-          acc = first ? __dmul_rn(K[j][i], cv) : fma(K[j][i], cv, acc);
-          first = false;
-        }
-      });
-    } else {
-      if constexpr (n == 1) {
-        acc = __dmul_rn(K[1][i], ni_cval<METHOD, ROW, 1>());
-        acc = ni_fma_term<METHOD, ROW, 0>(K[0][i], acc);
-        acc = ni_fma_term<METHOD, ROW, 2>(K[2][i], acc);
-        acc = ni_fma_term<METHOD, ROW, 3>(K[3][i], acc);
-      } else {
-        acc = __dadd_rn(ni_pair<METHOD, ROW, 0, 1>(K[0][i], K[1][i]), ni_pair<METHOD, ROW, 2, 3>(K[2][i], K[3][i]));
-      }
-      ni_static_for<4, COLS>([&](auto jj) {
-        constexpr int j = decltype(jj)::value;
-        acc = ni_fma_term<METHOD, ROW, j>(K[j][i], acc);
-      });
-    }
-    out[i] = acc;
-  }
+  for (int i = 0; i < n; ++i)
+    out[i] = ni_dot_col<METHOD, ROW, COLS, n == 1>([&](auto jj) { return K[decltype(jj)::value][i]; });
 }
 
 // _aux.py:71-75
@@ -269,7 +279,13 @@ NI_DEV double ni_rms(const double (&x)[n]) {
     return sqrt(acc / (double)n);
 }
 
-NI_DEV double ni_pow(double x, double e) { return pow(x, e); }
+// x ** error_exponent in select_initial_step (_basic.py:87): same correctly-rounded evaluation as the
+// controller where it applies, the library pow outside that range
+template <int K>
+NI_DEV double ni_pow_init(double x) {
+  if (x > 7.888609052210118e-31 && x < 1.2676506002282294e+30) return ni_pow_core<K>(x);
+  return pow(x, -1.0 / K);
+}
 
 // |nextafter(t, dir*inf) - t|  (_basic.py:139), for finite t
 NI_DEV double ni_ulp_eps(double t, double dir) {
@@ -307,7 +323,6 @@ NI_DEV bool ni_cond_test(const NiArgs &a, const double (&y)[n], const double *au
 template <class Rhs, int METHOD>
 NI_DEV void ni_small_init_body(const NiArgs &a) {
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
-  constexpr double err_exp = -1.0 / (NiTab<METHOD>::ORDER + 1);
   const long long N = a.N;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < N;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -343,7 +358,7 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
       if (d1 <= 1e-15 && d2 <= 1e-15)
         h1 = fmax(1e-6, __dmul_rn(h0, 1e-3));
       else
-        h1 = ni_pow(__dmul_rn(fmax(d1, d2), 100.0), err_exp);
+        h1 = ni_pow_init<NiTab<METHOD>::ORDER + 1>(__dmul_rn(fmax(d1, d2), 100.0));
       h_abs = fmin(__dmul_rn(100.0, h0), h1);
     } else {
       h_abs = fabs(a.first_step);
@@ -380,7 +395,6 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
   using Tab = NiTab<METHOD>;
   constexpr int S = Tab::S;
-  constexpr double err_exp = -1.0 / (Tab::ORDER + 1);  // _basic.py:234
   constexpr unsigned FULL = 0xffffffffu;
   const long long N = a.N;
   const unsigned lane = threadIdx.x & 31u;

@@ -1,0 +1,424 @@
+// ni_large.cuh -- one CTA per trajectory for large state dimension (method-of-lines systems).
+//
+// BASELINE config C5: n = 4096 heat / Burgers, RK45.  The working set of one attempt is
+// y, K0..K6, y_new = 9 vectors x 32 KB = 288 KB -- more than the 227 KB of shared memory and more
+// than the 256 KB register file, so it is split: every thread owns CPT CONTIGUOUS components and
+// keeps y, K0 (the FSAL stage), K2 and the stage input in registers, the remaining stage vectors
+// live in shared memory in a [slot][thread] layout (conflict-free 8-byte accesses).  Nothing of the
+// stage loop touches HBM: global traffic is y0 in, terminal state out, plus recorded steps.
+//
+// The right-hand side is a 3-point stencil functor
+//     Rhs::eval(t, y_left, y_centre, y_right, p) -> dy_j        (Dirichlet 0 outside 0..n-1)
+// so neighbours inside a thread come from registers; only the two edge values per thread go through
+// shared memory (double-buffered: one __syncthreads per RHS evaluation).  The RMS error norm is a
+// warp-shuffle reduction followed by a fixed-order sum of the per-warp partials.
+//
+// Semantics are those of ni_core.cuh (reference _basic.py:114-180 / _advanced.py:126-195); tableau
+// contractions use the same per-component order as the small kernels and the CPU oracle, the norm
+// uses a tree order (the reference's own n >= 4 order is host-BLAS/LLVM dependent, SURVEY.md
+// appendix B, so parity for n >= 4 is 1e-12 relative + identical step counts, not bitwise).
+#pragma once
+#include "ni_core.cuh"
+
+#define NI_LARGE_MAX_THREADS 512
+
+// p = (k): dy_j = k (y_{j-1} - 2 y_j + y_{j+1})
+struct NiStencilHeat {
+  static constexpr int P = 1, Q = 0;
+  NI_DEV static double eval(double, double ym, double yc, double yp, const double *p) {
+    return __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));
+  }
+};
+// p = (nu/dx^2, 1/(2dx)): dy_j = p0 (y_{j-1} - 2 y_j + y_{j+1}) - (y_j p1)(y_{j+1} - y_{j-1})
+struct NiStencilBurgers {
+  static constexpr int P = 2, Q = 0;
+  NI_DEV static double eval(double, double ym, double yc, double yp, const double *p) {
+    const double diff = __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));
+    return __dadd_rn(diff, -__dmul_rn(__dmul_rn(yc, p[1]), __dadd_rn(yp, -ym)));
+  }
+};
+
+// Which stage vectors stay in registers: K0 always (read by every stage), K2 for RK45 (5 reads).
+template <int METHOD, int J>
+struct NiKInReg {
+  static constexpr bool value = (J == 0) || (METHOD == NI_RK45 && J == 2);
+};
+// shared-memory slot of stage vector J (J = S is the new FSAL stage), slot count, and the slot of y_new
+template <int METHOD>
+struct NiLargeSlots;
+template <>
+struct NiLargeSlots<NI_RK45> {  // K1 K3 K4 K5 K6 | y_new
+  NI_HD static constexpr int slot(int j) { return j == 1 ? 0 : j - 2; }
+  static constexpr int KSLOTS = 5, TOTAL = 6;
+};
+template <>
+struct NiLargeSlots<NI_RK23> {  // K1 K2 K3 | y_new
+  NI_HD static constexpr int slot(int j) { return j - 1; }
+  static constexpr int KSLOTS = 3, TOTAL = 4;
+};
+
+// dynamic shared memory of one CTA, in doubles
+NI_HD constexpr size_t ni_large_smem_doubles(int method, int threads, int cpt) {
+  return (size_t)(method == NI_RK45 ? 6 : 4) * threads * cpt + 4 * (size_t)threads + 2 * 32 + 8;
+}
+
+struct NiLargeCtx {
+  double *vec;    // TOTAL slots of [CPT][T]
+  double *edge;   // [2 parity][2 sides][T]
+  double *part;   // [2 parity][32] per-warp partial sums
+  long long *bcast;
+  int T, tid, n, j0;
+};
+
+// neighbour exchange: returns y_{j0-1} and y_{j0+CPT} of this thread for the stage vector `v`
+template <int CPT>
+NI_DEV void ni_large_edges(const NiLargeCtx &c, const double (&v)[CPT], int parity, double &left, double &right) {
+  double *eL = c.edge + (parity * 2 + 0) * c.T, *eR = c.edge + (parity * 2 + 1) * c.T;
+  eL[c.tid] = v[0];
+  eR[c.tid] = v[CPT - 1];
+  __syncthreads();
+  left = c.tid > 0 ? eR[c.tid - 1] : 0.0;
+  right = c.tid + 1 < c.T ? eL[c.tid + 1] : 0.0;
+}
+
+// dy for the CPT components of this thread; components >= n stay exactly zero
+template <class Rhs, int CPT>
+NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], const double *p, int parity,
+                         double (&out)[CPT]) {
+  double left, right;
+  ni_large_edges<CPT>(c, v, parity, left, right);
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const double ym = i == 0 ? left : v[i - 1];
+    const double yp = i == CPT - 1 ? right : v[i + 1];
+    const double d = Rhs::eval(t, ym, v[i], yp, p);
+    out[i] = (c.j0 + i < c.n) ? d : 0.0;
+  }
+}
+
+// sum over the block of `x` (fixed order: lanes by butterfly, then warps sequentially); all threads get it
+NI_DEV double ni_large_block_sum(const NiLargeCtx &c, double x, int parity) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+  double *part = c.part + parity * 32;
+  if ((c.tid & 31) == 0) part[c.tid >> 5] = x;
+  __syncthreads();
+  double s = part[0];
+  const int nw = c.T >> 5;
+  for (int w = 1; w < nw; ++w) s = __dadd_rn(s, part[w]);
+  return s;
+}
+
+template <int CPT>
+NI_DEV double ni_large_rms(const NiLargeCtx &c, const double (&x)[CPT], int parity) {
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) acc = __dadd_rn(acc, __dmul_rn(x[i], x[i]));
+  return sqrt(ni_large_block_sum(c, acc, parity) / (double)c.n);
+}
+
+NI_DEV NiLargeCtx ni_large_ctx(const NiArgs &a, double *smem, int cpt, int total_slots) {
+  NiLargeCtx c;
+  c.T = blockDim.x;
+  c.tid = threadIdx.x;
+  c.n = a.n;
+  c.j0 = c.tid * cpt;
+  c.vec = smem;
+  c.edge = smem + (size_t)total_slots * c.T * cpt;
+  c.part = c.edge + 4 * c.T;
+  c.bcast = (long long *)(c.part + 64);
+  return c;
+}
+
+// ---------------------------------------------------------------- init (RK.__init__ + select_initial_step)
+template <class Rhs, int METHOD, int CPT>
+NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
+  constexpr int P = Rhs::P;
+  NiLargeCtx c = ni_large_ctx(a, smem, CPT, NiLargeSlots<METHOD>::TOTAL);
+  const int n = c.n;
+  for (long long idx = blockIdx.x; idx < a.N; idx += gridDim.x) {
+    double y[CPT], f0[CPT], p[P > 0 ? P : 1], rt[CPT], at[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int j = c.j0 + i;
+      y[i] = j < n ? a.y0_rows[idx * n + j] : 0.0;
+      rt[i] = j < n ? a.rtol_d[j] : 0.0;
+      at[i] = j < n ? a.atol_d[j] : 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = a.params_rows[idx * P + i];
+    const double t0 = a.t0[idx * a.t0_stride], tb = a.tb0[idx * a.tb_stride];
+    ni_large_rhs<Rhs, CPT>(c, t0, y, p, 0, f0);
+    const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
+    double h_abs;
+    if (a.first_step == 0.0) {
+      double scale[CPT], tmp[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        scale[i] = fma(fabs(y[i]), rt[i], at[i]);
+        tmp[i] = y[i] / scale[i];
+      }
+      const double d0 = ni_large_rms<CPT>(c, tmp, 0);
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) tmp[i] = f0[i] / scale[i];
+      const double d1 = ni_large_rms<CPT>(c, tmp, 1);
+      const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : __dmul_rn(0.01, d0) / d1;
+      const double hd = __dmul_rn(h0, dir);
+      double y1[CPT], f1[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) y1[i] = fma(hd, f0[i], y[i]);
+      ni_large_rhs<Rhs, CPT>(c, __dadd_rn(t0, hd), y1, p, 1, f1);
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) tmp[i] = __dadd_rn(f1[i], -f0[i]) / scale[i];
+      const double d2 = ni_large_rms<CPT>(c, tmp, 0) / h0;
+      double h1;
+      if (d1 <= 1e-15 && d2 <= 1e-15)
+        h1 = fmax(1e-6, __dmul_rn(h0, 1e-3));
+      else
+        h1 = ni_pow_init<NiTab<METHOD>::ORDER + 1>(__dmul_rn(fmax(d1, d2), 100.0));
+      h_abs = fmin(__dmul_rn(100.0, h0), h1);
+    } else {
+      h_abs = fabs(a.first_step);
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int j = c.j0 + i;
+      if (j < n) {
+        a.y[idx * n + j] = y[i];
+        a.klast[idx * n + j] = f0[i];
+      }
+    }
+    if (c.tid == 0) {
+      a.t[idx] = t0;
+      a.t_bound[idx] = tb;
+      a.direction[idx] = dir;
+      a.h_abs[idx] = h_abs;
+      a.step_size[idx] = __dmul_rn(dir, h_abs);
+#pragma unroll
+      for (int i = 0; i < P; ++i) a.params[idx * P + i] = p[i];
+      a.status[idx] = NI_ST_RUNNING;
+      a.n_acc[idx] = 0;
+      a.n_rej[idx] = 0;
+      a.running[idx] = 1;
+    }
+    __syncthreads();  // edge / partial buffers are reused by the next trajectory
+  }
+}
+
+// ---------------------------------------------------------------- run
+template <class Rhs, int METHOD, bool ADV, bool REC, int CPT>
+NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
+  constexpr int P = Rhs::P;
+  using Tab = NiTab<METHOD>;
+  using Slots = NiLargeSlots<METHOD>;
+  constexpr int S = Tab::S;
+  NiLargeCtx c = ni_large_ctx(a, smem, CPT, Slots::TOTAL);
+  const int n = c.n, T = c.T, tid = c.tid;
+  // shared stage vector J, component i of this thread
+  auto sv = [&](int slot, int i) -> double & { return c.vec[((size_t)slot * CPT + i) * T + tid]; };
+  constexpr int YN_SLOT = Slots::KSLOTS;
+
+  for (;;) {
+    // ---- next trajectory (one queue pop per CTA)
+    if (tid == 0) {
+      long long idx = (long long)atomicAdd(a.queue, 1ull);
+      if (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW)) idx = a.N;
+      c.bcast[0] = idx;
+    }
+    __syncthreads();
+    const long long idx = c.bcast[0];
+    __syncthreads();
+    if (idx >= a.N) break;
+    int status = a.status[idx];
+    if (status != NI_ST_RUNNING) {
+      if (tid == 0) a.running[idx] = 0;
+      continue;
+    }
+    double t = a.t[idx], h_abs = a.h_abs[idx], step_h = a.step_size[idx];
+    const double tb = a.t_bound[idx], dir = a.direction[idx];
+    double y[CPT], k0[CPT], k2[CPT], p[P > 0 ? P : 1];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int j = c.j0 + i;
+      y[i] = j < n ? a.y[idx * n + j] : 0.0;
+      k0[i] = j < n ? a.klast[idx * n + j] : 0.0;
+      k2[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = a.params[idx * P + i];
+    int nacc = a.n_acc[idx], nrej = a.n_rej[idx];
+    long long att_left = a.max_attempts, acc_left = a.max_accepts;
+    bool last_accept = false, fresh = true, done = false;
+    double eps = 0, min_step = 0;
+
+    while (!done) {
+      if (fresh) {  // step entry (_basic.py:135-143)
+        if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
+          step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
+          status = NI_ST_FINISHED;
+          last_accept = false;
+          break;
+        }
+        eps = ni_ulp_eps(t, dir);
+        min_step = __dmul_rn(8.0, eps);
+        if (h_abs < min_step) h_abs = min_step;
+        fresh = false;
+      }
+      // ---- one attempt (_basic.py:145-169)
+      const double h_pre = h_abs;
+      if (h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+      double h = ADV ? __dmul_rn(h_abs, dir) : h_abs;
+      double tn = __dadd_rn(t, h);
+      if (__dmul_rn(dir, __dadd_rn(tn, -tb)) >= 0.0) {
+        tn = tb;
+        h = __dadd_rn(tn, -t);
+        h_abs = fabs(h);
+      }
+      // K_j of component i: register-resident or shared
+      auto kget = [&](auto jj, int i) -> double {
+        constexpr int j = decltype(jj)::value;
+        if constexpr (j == 0)
+          return k0[i];
+        else if constexpr (NiKInReg<METHOD, j>::value)
+          return k2[i];
+        else
+          return sv(Slots::slot(j), i);
+      };
+      int parity = 0;
+      ni_static_for<1, S>([&](auto ss) {
+        constexpr int s = decltype(ss)::value;
+        double ys[CPT], ks[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const double d = ni_dot_col<METHOD, s, s, false>([&](auto jj) { return kget(jj, i); });
+          ys[i] = __dadd_rn(y[i], __dmul_rn(d, h));
+        }
+        ni_large_rhs<Rhs, CPT>(c, __dadd_rn(t, __dmul_rn(ni_cval<METHOD, 0, s>(), h)), ys, p, parity, ks);
+        parity ^= 1;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          if constexpr (NiKInReg<METHOD, s>::value)
+            k2[i] = ks[i];
+          else
+            sv(Slots::slot(s), i) = ks[i];
+        }
+      });
+      double yn[CPT], kn[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        const double d = ni_dot_col<METHOD, S, S, false>([&](auto jj) { return kget(jj, i); });
+        yn[i] = __dadd_rn(y[i], __dmul_rn(h, d));
+      }
+      ni_large_rhs<Rhs, CPT>(c, tn, yn, p, parity, kn);
+      parity ^= 1;
+      double sq = 0.0;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        sv(Slots::slot(S), i) = kn[i];
+        const int j = c.j0 + i;
+        const double ed = ni_dot_col<METHOD, S + 1, S + 1, false>([&](auto jj) {
+          if constexpr (decltype(jj)::value == S)
+            return kn[i];
+          else
+            return kget(jj, i);
+        });
+        const double rt = j < n ? __ldg(a.rtol_d + j) : 0.0, at = j < n ? __ldg(a.atol_d + j) : 1.0;
+        const double e = __dmul_rn(ed, h) / __dadd_rn(at, __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), rt));
+        sq = __dadd_rn(sq, __dmul_rn(e, e));
+      }
+      const double en = sqrt(ni_large_block_sum(c, sq, parity & 1) / (double)n);
+      --att_left;
+
+      // ---- controller + commit: uniform across the CTA
+      const bool ok = en < 1.0;
+      const bool nan = !ok && !(en >= 1.0);
+      bool park = false;
+      long long slot = -1;
+      if (REC && ok) {
+        if (tid == 0) c.bcast[1] = (long long)atomicAdd(a.rec_cursor, 1ull);
+        __syncthreads();
+        slot = c.bcast[1];
+        park = slot >= a.rec_cap;
+      }
+      const double sp = __dmul_rn(0.9, ni_pow_ctrl<Tab::ORDER + 1>(en));
+      const double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      const double h_new = __dmul_rn(h_abs, fac);
+      const bool fail = !ok && !nan && h_new < min_step;
+      const bool take = (ok && !park) || fail;
+      h_abs = park ? h_pre : (nan ? h_abs : h_new);
+      if (take) {
+        t = tn;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) y[i] = yn[i];
+      }
+      if (take || nan) step_h = h;
+      if (!park) {
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) k0[i] = kn[i];  // K[0] = K[-1] of the next attempt (stale after a reject)
+      }
+      const bool accepted = ok && !park;
+      if (accepted) {
+        ++nacc;
+        --acc_left;
+        if (REC) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i)
+            if (c.j0 + i < n) a.rec_y[slot * n + c.j0 + i] = y[i];
+          if (tid == 0) {
+            a.rec_traj[slot] = (unsigned int)idx;
+            a.rec_step[slot] = (unsigned int)nacc;
+            a.rec_t[slot] = t;
+          }
+        }
+      } else if (!park) {
+        ++nrej;
+      }
+      if (park) {
+        ++att_left;
+        if (tid == 0) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+      }
+      fresh = accepted;
+      last_accept = accepted;
+      if (fail) status = NI_ST_FAILED;
+      if (nan) status = NI_ST_NONFINITE;
+      done = park || fail || nan || att_left <= 0 || (accepted && acc_left <= 0);
+      if (accepted && !done && __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
+        step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);  // terminal step() of `while step(): pass`
+        status = NI_ST_FINISHED;
+        last_accept = false;
+        done = true;
+      }
+    }
+    // ---- retire
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int j = c.j0 + i;
+      if (j < n) {
+        a.y[idx * n + j] = y[i];
+        a.klast[idx * n + j] = k0[i];
+      }
+    }
+    if (tid == 0) {
+      a.t[idx] = t;
+      a.h_abs[idx] = h_abs;
+      a.step_size[idx] = step_h;
+      a.status[idx] = status;
+      a.n_acc[idx] = nacc;
+      a.n_rej[idx] = nrej;
+      a.running[idx] = last_accept ? 1 : 0;
+      if (status == NI_ST_RUNNING) atomicAdd(a.queue + 2, 1ull);
+      if (last_accept) atomicAdd(a.queue + 3, 1ull);
+    }
+  }
+}
+
+template <class Rhs, int METHOD, int CPT>
+__global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ni_k_large_init(const NiArgs a) {
+  extern __shared__ double ni_smem[];
+  ni_large_init_body<Rhs, METHOD, CPT>(a, ni_smem);
+}
+template <class Rhs, int METHOD, bool ADV, bool REC, int CPT>
+__global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ni_k_large_run(const NiArgs a) {
+  extern __shared__ double ni_smem[];
+  ni_large_run_body<Rhs, METHOD, ADV, REC, CPT>(a, ni_smem);
+}

@@ -1,4 +1,4 @@
-// ni_large_host.h -- host-side interface of the CTA-per-trajectory kernels (ni_large.cu).
+// ni_large_host.h -- host-side interface of the CTA-per-trajectory kernels (ni_large_*.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -7,13 +7,18 @@
 struct NiLargePlan {
   const void *k_init = nullptr;
   const void *k_run[2] = {nullptr, nullptr};  // [record]
-  int threads = 0;
+  int threads = 0, cpt = 0;
   size_t smem_bytes = 0;
-  int rhs_id = 0;
+  double *tol_d = nullptr;  // rtol[n] followed by atol[n] (owned by the ensemble)
 };
+
+struct NiLargeKernels {  // every instantiation for one stencil RHS
+  int P, Q;
+  const void *init[2][4];        // [method][log2 cpt]
+  const void *run[2][2][2][4];   // [method][advanced][record][log2 cpt]
+};
+const NiLargeKernels *ni_large_kernels_heat();
+const NiLargeKernels *ni_large_kernels_burgers();
 
 // Returns false when (rhs_id, n) has no CTA-per-trajectory kernel.
 bool ni_large_builtin(int rhs_id, int n, int method, int advanced, NiLargePlan *plan, int *P, int *Q);
-// Allocates what the plan needs on the current device (tolerance vectors, ...) and opts in to large shared memory.
-bool ni_large_prepare(NiLargePlan *plan, NiArgs *a, int n, int device, int sms);
-int ni_large_set_tolerances(NiLargePlan *plan, NiArgs *a, const double *rtol, const double *atol, int n, cudaStream_t s);

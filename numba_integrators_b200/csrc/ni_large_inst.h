@@ -1,0 +1,24 @@
+// Instantiates every (method, advanced, record, components-per-thread) variant for one stencil RHS.
+#pragma once
+#include "ni_large.cuh"
+#include "ni_large_host.h"
+#include "ni_host.h"
+
+#define NI_L_INIT(RHS, M) \
+  {(const void *)&ni_k_large_init<RHS, M, 1>, (const void *)&ni_k_large_init<RHS, M, 2>, \
+   (const void *)&ni_k_large_init<RHS, M, 4>, (const void *)&ni_k_large_init<RHS, M, 8>}
+#define NI_L_RUN(RHS, M, A, R) \
+  {(const void *)&ni_k_large_run<RHS, M, A, R, 1>, (const void *)&ni_k_large_run<RHS, M, A, R, 2>, \
+   (const void *)&ni_k_large_run<RHS, M, A, R, 4>, (const void *)&ni_k_large_run<RHS, M, A, R, 8>}
+#define NI_DEFINE_LARGE_KERNELS(FN, RHS)                                                             \
+  NI_VISIBLE_INTERNAL const NiLargeKernels *FN() {                                                   \
+    static const NiLargeKernels k = {                                                                \
+        RHS::P,                                                                                      \
+        RHS::Q,                                                                                      \
+        {NI_L_INIT(RHS, NI_RK23), NI_L_INIT(RHS, NI_RK45)},                                          \
+        {{{NI_L_RUN(RHS, NI_RK23, false, false), NI_L_RUN(RHS, NI_RK23, false, true)},               \
+          {NI_L_RUN(RHS, NI_RK23, true, false), NI_L_RUN(RHS, NI_RK23, true, true)}},                \
+         {{NI_L_RUN(RHS, NI_RK45, false, false), NI_L_RUN(RHS, NI_RK45, false, true)},               \
+          {NI_L_RUN(RHS, NI_RK45, true, false), NI_L_RUN(RHS, NI_RK45, true, true)}}}};              \
+    return &k;                                                                                       \
+  }
