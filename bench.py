@@ -117,9 +117,13 @@ def cpu_oracle_rate(w, seconds, threads=0):
                              rtol=w.rtol, atol=w.atol, advanced=w.advanced, nthreads=threads)
         return time.perf_counter() - t0, int(o['n_accepted'].sum())
 
-    dt, acc = run(n)  # calibration (also warms caches)
+    dt, acc = run(n)  # calibration (also warms caches): grow the sample until it runs for >= 0.5 s
+    while dt < 0.5 and n < w.N:
+        n = min(w.N, n * 4)
+        dt, acc = run(n)
     k = int(min(w.N, max(n, n * seconds / max(dt, 1e-3))))
-    dt, acc = run(k)
+    if k != n:
+        dt, acc = run(k)
     return acc / dt, k, threads, dt
 
 
@@ -211,7 +215,7 @@ def main():
     stream = torch.cuda.current_stream()
     ens.set_stream(stream.cuda_stream)
     if record:
-        ens.record_enable(int(N * 1000))
+        ens.record_enable(int(N * 1000))  # the whole ensemble's accepted steps stay in HBM (~877 per trajectory)
 
     # measured FP64 peak (MEASURED_PEAKS.json has HBM and bf16 only)
     pk = _lib.C.c_double(0)
@@ -263,6 +267,23 @@ def main():
     acc_all = float(tot[0].item())
     value = acc_all * args.steps / (ms_max * 1e-3)
 
+    # ---- the one collective of the path: final NCCL gather of terminal states + statistics (device buffers)
+    gather_ms = None
+    if world > 1:
+        from numba_integrators_b200 import distributed as nd
+        tens, small = nd.device_tensors(ens)
+        local = {k: (v.t().contiguous() if small and v.dim() == 2 else v) for k, v in tens.items()}
+        nd.all_gather_arrays(local)  # warm-up (NCCL channel setup)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        nd.all_gather_arrays(local)
+        g1.record()
+        barrier()
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gather_ms = float(gt.item())
+
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -308,13 +329,21 @@ def main():
     if rank == 0:
         flops = w.flops_per_attempt * att_rank  # algorithmic flops of one launch
         achieved = flops / (run_ms * 1e-3) / 1e12
+        kname = 'ni_k_large_run (CTA per trajectory)' if ens.kind else 'ni_k_run (thread per trajectory, persistent)'
         roofline = {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                     'frac': achieved / fp64_peak if fp64_peak else None, 'traffic': None,
-                    'kernel': 'ni_k_run (persistent fast-forward kernel)', 'kernel_ms': run_ms,
+                    'kernel': kname, 'kernel_ms': run_ms,
                     'flops_per_attempt': w.flops_per_attempt, 'attempts_per_launch': att_rank,
                     'peak_source': 'live DFMA-chain microbenchmark ni_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; '
                                    'nominal 37.2 TFLOP/s)',
                     'hbm_gbs_measured': peaks.get('hbm_gbs')}
+        if record:  # C2: recording-heavy -- report the HBM side of the ridge as well
+            rec_bytes = w.record_bytes_per_step * acc_rank
+            hbm = peaks.get('hbm_gbs') or 6650.0
+            roofline['hbm'] = {'bound': 'hbm', 'achieved': rec_bytes / (run_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                               'frac': rec_bytes / (run_ms * 1e-3) / 1e9 / hbm, 'bytes_per_accepted_step':
+                               w.record_bytes_per_step, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)'
+                               if peaks.get('hbm_gbs') else 'fallback 6650 GB/s'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -323,6 +352,8 @@ def main():
                            'l2': f'inputs {N * (n + ens.P) * 8 / 1e6:.0f} MB + state per launch exceed the 126 MB L2',
                            'accepted_per_traj': acc_rank / N, 'rejected_per_traj': (att_rank - acc_rank) / N},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline}
+        if gather_ms is not None:
+            line['final_gather_ms'] = gather_ms  # NCCL all_gather of t, y, aux, counters, status (not in a step)
         if world == 1 and not args.no_cpu_baseline:
             rate, k, threads, dt = cpu_oracle_rate(w, args.cpu_seconds)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',

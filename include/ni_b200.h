@@ -100,6 +100,9 @@ int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_module **o
 int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced, const char *nvrtc_options,
                       ni_module **out);
 int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages);
+/* device layout of the y / klast / aux / params buffers behind ni_ensemble_device_ptr:
+ * 0 = component-major [n][N] (thread-per-trajectory kernels), 1 = trajectory-major [N][n] (CTA-per-trajectory) */
+int ni_module_layout(const ni_module *m, int *layout);
 const char *ni_module_log(const ni_module *m);
 int ni_module_destroy(ni_module *m);
 

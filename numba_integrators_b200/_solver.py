@@ -150,6 +150,9 @@ class Ensemble:
         self.device = int(device)
 
         self._mod = self.fun._module(self.n, method, self._advanced)
+        kind = C.c_int(0)
+        check(self._L.ni_module_layout(self._mod, kind))
+        self.kind = kind.value  # 0: component-major device buffers, 1: trajectory-major
         h = _lib._vp()
         check(self._L.ni_ensemble_create(self._mod, self.device, self.N, h))
         self._h = h

@@ -262,6 +262,11 @@ NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *metho
   if (n_stages) *n_stages = m->S;
   return NI_OK;
 }
+NI_API int ni_module_layout(const ni_module *m, int *layout) {
+  if (!m || !layout) return fail(NI_ERR_INVALID, "module / layout is NULL");
+  *layout = m->kind;
+  return NI_OK;
+}
 NI_API const char *ni_module_log(const ni_module *m) { return m ? m->log.c_str() : ""; }
 NI_API int ni_module_destroy(ni_module *m) {
   if (!m) return NI_OK;

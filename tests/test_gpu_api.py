@@ -166,3 +166,26 @@ def test_user_rhs_snippet_matches_builtin():
     with pytest.raises(ni.NiError) as ei:
         ni.RK45(ni.CudaRHS('dy[0] = undefined_symbol;', n=1), 0.0, np.ones(1), 1.0)
     assert ei.value.code == -3
+
+
+def test_device_views_and_nccl_gather_single_rank():
+    """The final gather runs on the ensemble's own device buffers (zero-copy torch views) over NCCL."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from numba_integrators_b200 import distributed as nd, workloads as wl
+    w = wl.c3_lorenz(N=1000, t_bound=1.0)
+    ens = ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    ens.run()
+    tens, small = nd.device_tensors(ens)
+    assert small and tens['y'].shape == (3, 1000) and tens['y'].is_cuda
+    assert np.array_equal(tens['y'].t().cpu().numpy(), ens.y)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29533')
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))
+    try:
+        full = nd.gather(ens)
+    finally:
+        dist.destroy_process_group()
+    assert np.array_equal(full['y'], ens.y) and np.array_equal(full['t'], ens.t)
+    assert np.array_equal(full['auxiliary'], ens.auxiliary) and np.array_equal(full['n_accepted'], ens.n_accepted)
