@@ -142,7 +142,9 @@ int ni_ensemble_set_max_attempts(ni_ensemble *e, int64_t per_launch);
 
 /* ---- recording of accepted steps into an HBM append log --------------------------------
  * (README.md:62-69 appends solver.t / solver.y after every accepted step.)  Records are
- * (trajectory, step index, t, y[n], aux[Q]); order within the log is arbitrary. */
+ * (trajectory, step index, t, y[n], aux[Q]); order within the log is arbitrary.  record_count gives the
+ * number of log SLOTS in use (an upper bound: warps reserve slots in chunks); record_drain needs buffers for
+ * that many records, drops the unused slots and returns the number of real records in *n_out. */
 int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity);
 int ni_ensemble_record_count(ni_ensemble *e, int64_t *count);
 int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, double *t, double *y, double *aux,

@@ -184,9 +184,9 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false";
   src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
          "ni_small_init_body<NiUserRhs, " + M + ">(a); }\n";
-  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_run(const NiArgs a) { "
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run(const NiArgs a) { "
          "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false>(a); }\n";
-  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_run_rec(const NiArgs a) { "
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
          "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true>(a); }\n";
 
   nvrtcProgram prog = nullptr;
@@ -533,6 +533,9 @@ static int launch_run(ni_ensemble *e, int64_t max_accepts, bool timed) {
   if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
   e->a.max_accepts = max_accepts;
   e->a.max_attempts = e->max_attempts;
+  // record slots: warps of a long fast-forward reserve 512 at a time (one global cursor cannot serve ~1e9
+  // reservations/s); lock-step calls and small ensembles reserve exactly what they write
+  e->a.rec_chunk = (max_accepts == 1 || e->N < 65536 || e->mod.kind != NI_KIND_SMALL) ? 0 : 512;
   CU(cudaMemsetAsync(e->a.queue, 0, sizeof(unsigned long long) * 8, e->stream));
   const bool rec = e->a.rec_cap > 0;
   if (timed) CU(cudaEventRecord(e->ev[2], e->stream));
@@ -774,6 +777,7 @@ NI_API int ni_ensemble_record_count(ni_ensemble *e, int64_t *count) {
 NI_API int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, double *t, double *y, double *aux,
                                     int64_t max_records, int64_t *n_out) {
   if (!e || !n_out) return fail(NI_ERR_INVALID, "ensemble / n_out is NULL");
+  if (!traj) return fail(NI_ERR_INVALID, "the traj buffer is required (it marks unused slots)");
   int64_t count = 0;
   if (int rc = ni_ensemble_record_count(e, &count)) return rc;
   if (count > max_records) return fail(NI_ERR_INVALID, "host buffers hold %lld records, the log has %lld", (long long)max_records, (long long)count);
@@ -808,7 +812,23 @@ NI_API int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *st
   }
   CU(cudaMemsetAsync(a.rec_cursor, 0, sizeof(unsigned long long), e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  *n_out = count;
+  // drop the slots that were reserved in chunks but never written (rec_traj == NI_REC_INVALID)
+  int64_t kept = count;
+  if (traj) {
+    kept = 0;
+    for (int64_t i = 0; i < count; ++i) {
+      if (traj[i] == NI_REC_INVALID) continue;
+      if (kept != i) {
+        traj[kept] = traj[i];
+        if (step) step[kept] = step[i];
+        if (t) t[kept] = t[i];
+        if (y) memcpy(y + kept * n, y + i * n, sizeof(double) * n);
+        if (aux && Q > 0) memcpy(aux + kept * Q, aux + i * Q, sizeof(double) * Q);
+      }
+      ++kept;
+    }
+  }
+  *n_out = kept;
   return NI_OK;
 }
 

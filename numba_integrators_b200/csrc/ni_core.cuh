@@ -35,9 +35,18 @@
 #define NI_ST_NONFINITE 3  // error norm is NaN (the reference would spin forever)
 
 #define NI_MAX_SMALL_N 16
+#ifndef NI_BLOCK
 #define NI_BLOCK 128
+#endif
+// resident CTAs per SM the register allocator must allow for the run kernel: 6 x 128 threads (80 registers)
+// measured best for n <= 3 (+10 % over the unconstrained 90 registers / 5 CTAs on C3); larger systems keep
+// all their stage vectors in registers and take what they need
+#ifndef NI_MIN_BLOCKS
+#define NI_MIN_BLOCKS(n) ((n) <= 3 ? 6 : 1)
+#endif
 
 #define NI_FLAG_REC_OVERFLOW 1ull
+#define NI_REC_INVALID 0xffffffffu  // rec_traj value of a reserved-but-unused record slot
 
 #define NI_DEV __device__ __forceinline__
 #define NI_HD __host__ __device__
@@ -67,6 +76,7 @@ struct NiArgs {
   // recording of accepted steps (append log, SoA, capacity rec_cap records)
   unsigned long long *rec_cursor;
   long long rec_cap;
+  long long rec_chunk;          // slots a warp reserves per atomicAdd (0: exactly as many as it needs)
   unsigned int *rec_traj, *rec_step;
   double *rec_t, *rec_y, *rec_aux;  // rec_y [n][rec_cap], rec_aux [Q][rec_cap]
   // ff2cond: built-in predicate parameters
@@ -405,6 +415,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
   int nacc = 0, nrej = 0, status = NI_ST_RUNNING;
   long long att_left = 0, acc_left = 0;
+  long long rc_next = 0, rc_end = 0;  // REC: this warp's reserved slot range [rc_next, rc_end)
 
   auto retire = [&]() {
     a.t[idx] = t;
@@ -527,16 +538,34 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       --att_left;
     }
 
-    // ---- record log: reserve one slot per accepting lane (warp-aggregated append)
+    // ---- record log: one slot per accepting lane.  A warp reserves `rec_chunk` slots with ONE atomicAdd
+    // and hands them out locally (a single global cursor saturates the L2 atomic unit at ~0.8 G
+    // reservations/s: config C2 was bound by it); rec_chunk == 0 reserves exactly popc(mask) per iteration
+    // (lock-step ni.step, where a chunk would be abandoned after one use).  Slots of an abandoned chunk are
+    // marked NI_REC_INVALID so that the drain can skip them.
     long long slot = -1;
     if (REC) {
       const unsigned m = __ballot_sync(FULL, ok);
       if (m) {
-        const int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(a.rec_cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        if (ok) slot = (long long)(base + __popc(m & ((1u << lane) - 1u)));
+        const int cnt = __popc(m);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        const long long room = rc_end - rc_next;  // uniform across the warp
+        long long nb = rc_next;
+        if (cnt > room) {
+          const unsigned long long want = a.rec_chunk > 0 ? (unsigned long long)a.rec_chunk : (unsigned long long)(cnt - room);
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(a.rec_cursor, want);
+          nb = (long long)__shfl_sync(FULL, base, 0);
+        }
+        if (ok) slot = rank < room ? rc_next + rank : nb + (rank - room);
+        if (cnt > room) {
+          const long long want = a.rec_chunk > 0 ? a.rec_chunk : (long long)(cnt - room);
+          rc_next = nb + (cnt - room);
+          rc_end = nb + want < a.rec_cap ? nb + want : (nb < a.rec_cap ? a.rec_cap : nb);
+          if (rc_next > rc_end) rc_next = rc_end;
+        } else {
+          rc_next += cnt;
+        }
       }
     }
 
@@ -599,6 +628,9 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       if (done) retire();
     }
   }
+  if (REC) {  // slots reserved but never written
+    for (long long sidx = rc_next + lane; sidx < rc_end; sidx += 32) a.rec_traj[sidx] = NI_REC_INVALID;
+  }
 }
 
 // ---------------------------------------------------------------- kernel entry points
@@ -607,6 +639,6 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_k_init(const NiArgs a) {
   ni_small_init_body<Rhs, METHOD>(a);
 }
 template <class Rhs, int METHOD, bool ADV, bool REC>
-__global__ void __launch_bounds__(NI_BLOCK) ni_k_run(const NiArgs a) {
+__global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(Rhs::N)) ni_k_run(const NiArgs a) {
   ni_small_run_body<Rhs, METHOD, ADV, REC>(a);
 }

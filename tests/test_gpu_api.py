@@ -189,3 +189,37 @@ def test_device_views_and_nccl_gather_single_rank():
         dist.destroy_process_group()
     assert np.array_equal(full['y'], ens.y) and np.array_equal(full['t'], ens.t)
     assert np.array_equal(full['auxiliary'], ens.auxiliary) and np.array_equal(full['n_accepted'], ens.n_accepted)
+
+
+def test_user_rhs_n8_coupled_oscillators_against_scipy_like_accuracy():
+    """A user snippet with n = 8 (stage vectors still in registers): chain of coupled oscillators,
+    energy is conserved to the tolerance; ragged ensemble size (not a multiple of the warp)."""
+    body = '''
+        for (int i = 0; i < 4; ++i) {
+            const double left = i > 0 ? y[i - 1] : 0.0, right = i < 3 ? y[i + 1] : 0.0;
+            dy[i] = y[4 + i];
+            dy[4 + i] = p[0] * (left - 2.0 * y[i] + right);
+        }
+        double e = 0.0;
+        for (int i = 0; i < 4; ++i) e += 0.5 * y[4 + i] * y[4 + i];
+        for (int i = 0; i <= 4; ++i) {
+            const double a = i < 4 ? y[i] : 0.0, b = i > 0 ? y[i - 1] : 0.0;
+            e += 0.5 * p[0] * (a - b) * (a - b);
+        }
+        aux[0] = e;
+    '''
+    rng = np.random.default_rng(5)
+    N = 77
+    y0 = rng.uniform(-1, 1, size=(N, 8))
+    k = rng.uniform(0.5, 2.0, size=(N, 1))
+    f = ni.CudaRHS(body, n=8, P=1, Q=1, name='chain8')
+    s = ni.Advanced(1, 1, ni.RK45)(f, 0.0, y0, k, 10.0, rtol=1e-10, atol=1e-10)
+    e0 = s.auxiliary[:, 0].copy()
+    assert s.run() == 0
+    assert np.all(s.t == 10.0) and np.all(s.status == 1)
+    assert np.max(np.abs(s.auxiliary[:, 0] - e0) / e0) < 1e-7
+    # lock-step and fast-forward give identical bits
+    s2 = ni.Advanced(1, 1, ni.RK45)(f, 0.0, y0, k, 10.0, rtol=1e-10, atol=1e-10)
+    while ni.step(s2):
+        pass
+    assert np.array_equal(s2.y, s.y) and np.array_equal(s2.n_accepted, s.n_accepted)
