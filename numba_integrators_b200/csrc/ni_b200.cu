@@ -490,6 +490,11 @@ NI_API int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *a
       e->a.atol[i] = atol[i];
     }
   } else {
+    bool uni = true;
+    for (int i = 1; i < n; ++i) uni = uni && rtol[i] == rtol[0] && atol[i] == atol[0];
+    e->a.tol_uniform = uni ? 1 : 0;
+    e->a.rtol[0] = rtol[0];
+    e->a.atol[0] = atol[0];
     CU(cudaMemcpyAsync(e->mod.large.tol_d, rtol, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->mod.large.tol_d + n, atol, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));  // rtol / atol are caller-owned host buffers

@@ -70,6 +70,7 @@ struct NiArgs {
   double rtol[NI_MAX_SMALL_N], atol[NI_MAX_SMALL_N];
   int n;                        // large kernels: state dimension (run-time)
   const double *rtol_d, *atol_d;  // large kernels: tolerance vectors in HBM (n entries)
+  int tol_uniform;              // large kernels: every component has rtol[0] / atol[0]
   unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted
   long long max_attempts;       // per trajectory per launch (bounds kernel time)
   long long max_accepts;        // 1 = lock-step ni.step(), huge = fast-forward

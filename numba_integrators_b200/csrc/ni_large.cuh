@@ -57,9 +57,11 @@ struct NiLargeSlots<NI_RK23> {  // K1 K2 K3 | y_new
   static constexpr int KSLOTS = 3, TOTAL = 4;
 };
 
-// dynamic shared memory of one CTA, in doubles
+// dynamic shared memory of one CTA, in doubles.  Stage vectors are laid out [slot][component][NI_LARGE_MAX_THREADS]
+// whatever the CTA size, so that every access is `thread base + immediate offset`.
 NI_HD constexpr size_t ni_large_smem_doubles(int method, int threads, int cpt) {
-  return (size_t)(method == NI_RK45 ? 6 : 4) * threads * cpt + 4 * (size_t)threads + 2 * 32 + 8;
+  (void)threads;
+  return (size_t)(method == NI_RK45 ? 6 : 4) * NI_LARGE_MAX_THREADS * cpt + 4 * (size_t)NI_LARGE_MAX_THREADS + 2 * 32 + 8;
 }
 
 struct NiLargeCtx {
@@ -68,12 +70,13 @@ struct NiLargeCtx {
   double *part;   // [2 parity][32] per-warp partial sums
   long long *bcast;
   int T, tid, n, j0;
+  bool full;  // n == T * CPT: no padding components, masks are skipped
 };
 
 // neighbour exchange: returns y_{j0-1} and y_{j0+CPT} of this thread for the stage vector `v`
 template <int CPT>
 NI_DEV void ni_large_edges(const NiLargeCtx &c, const double (&v)[CPT], int parity, double &left, double &right) {
-  double *eL = c.edge + (parity * 2 + 0) * c.T, *eR = c.edge + (parity * 2 + 1) * c.T;
+  double *eL = c.edge + (parity * 2 + 0) * NI_LARGE_MAX_THREADS, *eR = c.edge + (parity * 2 + 1) * NI_LARGE_MAX_THREADS;
   eL[c.tid] = v[0];
   eR[c.tid] = v[CPT - 1];
   __syncthreads();
@@ -91,8 +94,11 @@ NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], 
   for (int i = 0; i < CPT; ++i) {
     const double ym = i == 0 ? left : v[i - 1];
     const double yp = i == CPT - 1 ? right : v[i + 1];
-    const double d = Rhs::eval(t, ym, v[i], yp, p);
-    out[i] = (c.j0 + i < c.n) ? d : 0.0;
+    out[i] = Rhs::eval(t, ym, v[i], yp, p);
+  }
+  if (!c.full) {
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) out[i] = (c.j0 + i < c.n) ? out[i] : 0.0;
   }
 }
 
@@ -123,9 +129,10 @@ NI_DEV NiLargeCtx ni_large_ctx(const NiArgs &a, double *smem, int cpt, int total
   c.tid = threadIdx.x;
   c.n = a.n;
   c.j0 = c.tid * cpt;
+  c.full = a.n == (int)blockDim.x * cpt;
   c.vec = smem;
-  c.edge = smem + (size_t)total_slots * c.T * cpt;
-  c.part = c.edge + 4 * c.T;
+  c.edge = smem + (size_t)total_slots * NI_LARGE_MAX_THREADS * cpt;
+  c.part = c.edge + 4 * NI_LARGE_MAX_THREADS;
   c.bcast = (long long *)(c.part + 64);
   return c;
 }
@@ -215,7 +222,8 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
   NiLargeCtx c = ni_large_ctx(a, smem, CPT, Slots::TOTAL);
   const int n = c.n, T = c.T, tid = c.tid;
   // shared stage vector J, component i of this thread
-  auto sv = [&](int slot, int i) -> double & { return c.vec[((size_t)slot * CPT + i) * T + tid]; };
+  double *const svb = c.vec + tid;
+  auto sv = [&](int slot, int i) -> double & { return svb[(slot * CPT + i) * NI_LARGE_MAX_THREADS]; };
   constexpr int YN_SLOT = Slots::KSLOTS;
 
   for (;;) {
@@ -322,7 +330,14 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
           else
             return kget(jj, i);
         });
-        const double rt = j < n ? __ldg(a.rtol_d + j) : 0.0, at = j < n ? __ldg(a.atol_d + j) : 1.0;
+        double rt = a.rtol[0], at = a.atol[0];  // uniform tolerances come from the constant bank
+        if (!a.tol_uniform) {
+          rt = j < n ? __ldg(a.rtol_d + j) : 0.0;
+          at = j < n ? __ldg(a.atol_d + j) : 1.0;
+        } else if (!c.full && j >= n) {
+          rt = 0.0;
+          at = 1.0;
+        }
         const double e = __dmul_rn(ed, h) / __dadd_rn(at, __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), rt));
         sq = __dadd_rn(sq, __dmul_rn(e, e));
       }
