@@ -337,6 +337,14 @@ def main():
                     'peak_source': 'live DFMA-chain microbenchmark ni_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; '
                                    'nominal 37.2 TFLOP/s)',
                     'hbm_gbs_measured': peaks.get('hbm_gbs')}
+        try:  # DRAM traffic of this kernel measured by ncu (profiles/), scaled to this launch's trajectory count
+            tr = json.loads((ROOT / 'profiles' / 'r01_dram_traffic.json').read_text()).get(args.workload)
+            if tr:
+                roofline['traffic'] = tr['bytes_per_trajectory'] * N
+                roofline['traffic_source'] = tr['capture']
+                roofline['algorithmic_bytes'] = N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13)
+        except (OSError, ValueError):
+            pass
         if record:  # C2: recording-heavy -- report the HBM side of the ridge as well
             rec_bytes = w.record_bytes_per_step * acc_rank
             hbm = peaks.get('hbm_gbs') or 6650.0
