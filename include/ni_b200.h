@@ -74,6 +74,12 @@ extern "C" {
 #define NI_F_DIRECTION 11 /* double[N]                                            */
 #define NI_F_PARAMS 12    /* double[N][P]                                         */
 #define NI_F_COND_HIT 13  /* uint8[N]  ff2cond predicate hit                      */
+/* record log buffers (ni_ensemble_device_ptr only; capacity entries, see the recording section) */
+#define NI_F_REC_TRAJ 20  /* uint32[cap]                                          */
+#define NI_F_REC_STEP 21  /* uint32[cap]                                          */
+#define NI_F_REC_T 22     /* double[cap]                                          */
+#define NI_F_REC_Y 23     /* double [n][cap] (layout 0) or [cap][n] (layout 1)    */
+#define NI_F_REC_AUX 24   /* double [Q][cap] (layout 0) or [cap][Q] (layout 1)    */
 
 /* predicates for ni_ensemble_ff2cond (checked after every accepted step, _API.py:41-49) */
 #define NI_COND_Y_GT 1
@@ -99,6 +105,11 @@ int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_module **o
  * in CUDA C++; it is fused into the stepper kernels with NVRTC for sm_100a. */
 int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced, const char *nvrtc_options,
                       ni_module **out);
+/* Large systems (n <= 4096) whose RHS is a 3-point stencil: `stencil_body` is the body of
+ *   __device__ double rhs_j(double t, double ym, double yc, double yp, const double* p, int j, int n)
+ * returning dy_j from y_{j-1}, y_j, y_{j+1} (zero outside 0..n-1); fused into the CTA-per-trajectory kernels. */
+int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int advanced,
+                              const char *nvrtc_options, ni_module **out);
 int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages);
 /* device layout of the y / klast / aux / params buffers behind ni_ensemble_device_ptr:
  * 0 = component-major [n][N] (thread-per-trajectory kernels), 1 = trajectory-major [N][n] (CTA-per-trajectory) */

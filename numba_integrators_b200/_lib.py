@@ -16,6 +16,7 @@ NI_OK, NI_ERR_INVALID, NI_ERR_CUDA, NI_ERR_NVRTC, NI_ERR_UNSUPPORTED, NI_ERR_NOM
 RK23, RK45 = 0, 1
 (F_T, F_Y, F_AUX, F_H_ABS, F_STEP_SIZE, F_KLAST, F_STATUS, F_N_ACCEPTED, F_N_REJECTED, F_RUNNING, F_T_BOUND,
  F_DIRECTION, F_PARAMS, F_COND_HIT) = range(14)
+F_REC_TRAJ, F_REC_STEP, F_REC_T, F_REC_Y, F_REC_AUX = 20, 21, 22, 23, 24  # device_ptr only (record log)
 ST_RUNNING, ST_FINISHED, ST_FAILED, ST_NONFINITE = 0, 1, 2, 3
 COND_Y_GT, COND_Y_LT, COND_AUX_GT, COND_AUX_LT = 1, 2, 3, 4
 
@@ -31,6 +32,7 @@ SIGNATURES = {
     'ni_module_builtin': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     'ni_module_compile': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
                                     C.POINTER(_vp)]),
+    'ni_module_compile_stencil': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)]),
     'ni_module_info': (C.c_int, [_vp] + [C.POINTER(C.c_int)] * 6),
     'ni_module_layout': (C.c_int, [_vp, C.POINTER(C.c_int)]),
     'ni_module_log': (C.c_char_p, [_vp]),

@@ -82,6 +82,29 @@ class CudaRHS(RHS):
         return f'CudaRHS({self.name!r}, n={self.n}, P={self.P}, Q={self.Q})'
 
 
+class CudaStencilRHS(RHS):
+    """User right-hand side of a large 1-D method-of-lines system (n <= 4096): the body of
+
+        __device__ double rhs_j(double t, double ym, double yc, double yp, const double* p, int j, int n)
+
+    returning dy_j from y_{j-1}, y_j, y_{j+1} (zero outside 0..n-1).  Fused into the CTA-per-trajectory
+    kernels with NVRTC; n is taken from y0."""
+
+    def __init__(self, body, P=0, parameters=None, name='user_stencil', nvrtc_options=''):
+        self.body, self.P, self.Q, self.n, self.name = str(body), int(P), 0, None, name
+        self.nvrtc_options = nvrtc_options
+        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
+
+    def _module(self, n, method, advanced):
+        out = _lib._vp()
+        _lib.check(_lib.lib().ni_module_compile_stencil(self.body.encode(), int(n), self.P, int(method),
+                                                        int(bool(advanced)), self.nvrtc_options.encode(), out))
+        return out
+
+    def __repr__(self):
+        return f'CudaStencilRHS({self.name!r}, P={self.P})'
+
+
 harmonic = BuiltinRHS('harmonic')
 sine = harmonic
 lorenz63 = BuiltinRHS('lorenz63')

@@ -97,6 +97,19 @@ class Records:
         m = r.traj == i
         return r.t[m], r.y[m], r.aux[m]
 
+    def to_npz(self, path):
+        """Write the records to a compressed .npz (columns traj, step, t, y, aux)."""
+        np.savez_compressed(path, traj=self.traj, step=self.step, t=self.t, y=self.y, aux=self.aux)
+
+    def to_parquet(self, path):
+        """Write the records to a Parquet file: one row per accepted step, columns traj, step, t, y0.., aux0.."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        cols = {'traj': self.traj, 'step': self.step, 't': self.t}
+        cols.update({f'y{i}': np.ascontiguousarray(self.y[:, i]) for i in range(self.y.shape[1])})
+        cols.update({f'aux{i}': np.ascontiguousarray(self.aux[:, i]) for i in range(self.aux.shape[1])})
+        pq.write_table(pa.table(cols), path)
+
 
 class Ensemble:
     """Device-resident solver state: N trajectories of one ODE on one GPU.
@@ -316,6 +329,26 @@ class Ensemble:
                                                y.ctypes.data, aux.ctypes.data if self.Q else None, c, n_out))
         k = n_out.value
         return Records(traj[:k], step[:k], t[:k], y[:k], aux[:k])
+
+    def record_views(self):
+        """Zero-copy torch views of the HBM record log for device-side consumers: dict with `count` (slots in
+        use), traj, step (uint32 viewed as int32), t, y, aux.  Layout: y is [n][capacity] for the
+        thread-per-trajectory kernels, [capacity][n] for the CTA-per-trajectory ones; slots whose traj is -1
+        (0xffffffff) were reserved but not written."""
+        import torch
+        from .distributed import _DeviceView
+        cap, count = self._rec_cap, self.record_count()
+        dev = torch.device('cuda', self.device)
+
+        def view(field, shape, ts):
+            return torch.as_tensor(_DeviceView(self.device_pointer(field), shape, ts), device=dev)
+        small = self.kind == 0
+        out = {'count': count, 'traj': view(_lib.F_REC_TRAJ, (cap,), '<i4'), 'step': view(_lib.F_REC_STEP, (cap,), '<i4'),
+               't': view(_lib.F_REC_T, (cap,), '<f8'),
+               'y': view(_lib.F_REC_Y, (self.n, cap) if small else (cap, self.n), '<f8')}
+        if self.Q:
+            out['aux'] = view(_lib.F_REC_AUX, (self.Q, cap) if small else (cap, self.Q), '<f8')
+        return out
 
     # ------------------------------------------------------------------ misc
     def device_pointer(self, field):

@@ -25,6 +25,7 @@
 
 extern const char ni_core_source[];   // ni_core.cuh as a string (generated: ni_core_src.cpp)
 extern const char ni_math_source[];   // ni_math.cuh as a string
+extern const char ni_large_source[];  // ni_large.cuh as a string
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -160,39 +161,13 @@ static int load_nvrtc() {
   return NI_OK;
 }
 
-NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced,
-                             const char *nvrtc_options, ni_module **out) {
-  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
-  *out = nullptr;
-  if (!rhs_body) return fail(NI_ERR_INVALID, "rhs_body is NULL");
-  if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
-  if (n < 1 || P < 0 || Q < 0) return fail(NI_ERR_INVALID, "need n >= 1, P >= 0, Q >= 0");
-  if (n > NI_MAX_SMALL_N)
-    return fail(NI_ERR_UNSUPPORTED, "user RHS snippets support n <= %d (got %d); larger systems use the built-in "
-                "method-of-lines kernels", NI_MAX_SMALL_N, n);
+// Compiles `src` (which includes the embedded kernel headers) for sm_100a and loads the three entry points.
+static int compile_and_load(const std::string &src, const char *nvrtc_options, const char *const names[3], ni_module *m) {
   if (int rc = load_nvrtc()) return rc;
-  advanced = advanced ? 1 : 0;
-
-  std::string src;
-  src += "#include \"ni_core.cuh\"\n";
-  src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
-         ", Q = " + std::to_string(Q) + ";\n";
-  src += "  NI_DEV static void eval(double t, const double* y, const double* p, double* dy, double* aux) {\n";
-  src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
-  src += rhs_body;
-  src += "\n  }\n};\n";
-  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false";
-  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
-         "ni_small_init_body<NiUserRhs, " + M + ">(a); }\n";
-  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run(const NiArgs a) { "
-         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false>(a); }\n";
-  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
-         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true>(a); }\n";
-
   nvrtcProgram prog = nullptr;
-  const char *hdr_src[] = {ni_core_source, ni_math_source};
-  const char *hdr_name[] = {"ni_core.cuh", "ni_math.cuh"};
-  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 2, hdr_src, hdr_name);
+  const char *hdr_src[] = {ni_core_source, ni_math_source, ni_large_source};
+  const char *hdr_name[] = {"ni_core.cuh", "ni_math.cuh", "ni_large.cuh"};
+  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 3, hdr_src, hdr_name);
   if (rc) return fail(NI_ERR_NVRTC, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(rc));
   std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
                                    "-default-device"};
@@ -209,7 +184,6 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   std::vector<const char *> copts;
   for (auto &s : opts) copts.push_back(s.c_str());
   rc = g_nvrtc.CompileProgram(prog, (int)copts.size(), copts.data());
-  ni_module *m = new ni_module;
   size_t lsz = 0;
   if (g_nvrtc.GetProgramLogSize(prog, &lsz) == 0 && lsz > 1) {
     m->log.resize(lsz);
@@ -218,7 +192,6 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   if (rc) {
     int code = fail(NI_ERR_NVRTC, "nvrtcCompileProgram: %s\n%s", g_nvrtc.GetErrorString(rc), m->log.c_str());
     g_nvrtc.DestroyProgram(&prog);
-    delete m;
     return code;
   }
   size_t csz = 0;
@@ -228,15 +201,51 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   g_nvrtc.DestroyProgram(&prog);
 
   cudaError_t ce = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-  cudaKernel_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
-  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&k0, m->lib, "ni_user_init");
-  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&k1, m->lib, "ni_user_run");
-  if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&k2, m->lib, "ni_user_run_rec");
+  cudaKernel_t k[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaLibraryGetKernel(&k[i], m->lib, names[i]);
   if (ce != cudaSuccess) {
     int code = fail(NI_ERR_CUDA, "loading the compiled RHS module: %s", cudaGetErrorString(ce));
     if (m->lib) cudaLibraryUnload(m->lib);
-    delete m;
+    m->lib = nullptr;
     return code;
+  }
+  m->k_init = (const void *)k[0];
+  m->k_run[0] = (const void *)k[1];
+  m->k_run[1] = (const void *)k[2];
+  return NI_OK;
+}
+
+NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced,
+                             const char *nvrtc_options, ni_module **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!rhs_body) return fail(NI_ERR_INVALID, "rhs_body is NULL");
+  if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
+  if (n < 1 || P < 0 || Q < 0) return fail(NI_ERR_INVALID, "need n >= 1, P >= 0, Q >= 0");
+  if (n > NI_MAX_SMALL_N)
+    return fail(NI_ERR_UNSUPPORTED, "dense user RHS snippets support n <= %d (got %d); larger systems must be "
+                "3-point stencils (ni_module_compile_stencil)", NI_MAX_SMALL_N, n);
+  advanced = advanced ? 1 : 0;
+  std::string src;
+  src += "#include \"ni_core.cuh\"\n";
+  src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
+         ", Q = " + std::to_string(Q) + ";\n";
+  src += "  NI_DEV static void eval(double t, const double* y, const double* p, double* dy, double* aux) {\n";
+  src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
+  src += rhs_body;
+  src += "\n  }\n};\n";
+  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false";
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
+         "ni_small_init_body<NiUserRhs, " + M + ">(a); }\n";
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run(const NiArgs a) { "
+         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false>(a); }\n";
+  src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
+         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true>(a); }\n";
+  ni_module *m = new ni_module;
+  const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
+  if (int rc = compile_and_load(src, nvrtc_options, names, m)) {
+    delete m;
+    return rc;
   }
   m->kind = NI_KIND_SMALL;
   m->n = n;
@@ -245,9 +254,59 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   m->method = method;
   m->advanced = advanced;
   m->S = method == NI_RK45 ? 6 : 3;
-  m->k_init = (const void *)k0;
-  m->k_run[0] = (const void *)k1;
-  m->k_run[1] = (const void *)k2;
+  *out = m;
+  return NI_OK;
+}
+
+NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int advanced,
+                                     const char *nvrtc_options, ni_module **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!stencil_body) return fail(NI_ERR_INVALID, "stencil_body is NULL");
+  if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
+  if (P < 0) return fail(NI_ERR_INVALID, "need P >= 0");
+  int lg = 0, threads = 0;
+  size_t smem = 0;
+  if (!ni_large_dims(n, method, &lg, &threads, &smem))
+    return fail(NI_ERR_UNSUPPORTED, "stencil systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_THREADS * 8, n);
+  advanced = advanced ? 1 : 0;
+  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false",
+                    C = std::to_string(1 << lg);
+  std::string src;
+  src += "#include \"ni_large.cuh\"\n";
+  src += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P) + ", Q = 0;\n";
+  src += "  NI_DEV static double eval(double t, double ym, double yc, double yp, const double* p, int j, int n) {\n";
+  src += "    (void)t; (void)ym; (void)yc; (void)yp; (void)p; (void)j; (void)n;\n";
+  src += stencil_body;
+  src += "\n  }\n};\n";
+  const std::string lb = "extern \"C\" __global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ";
+  src += lb + "ni_user_init(const NiArgs a) { extern __shared__ double s[]; ni_large_init_body<NiUserStencil, " + M +
+         ", " + C + ">(a, s); }\n";
+  src += lb + "ni_user_run(const NiArgs a) { extern __shared__ double s[]; ni_large_run_body<NiUserStencil, " + M +
+         ", " + A + ", false, " + C + ">(a, s); }\n";
+  src += lb + "ni_user_run_rec(const NiArgs a) { extern __shared__ double s[]; ni_large_run_body<NiUserStencil, " + M +
+         ", " + A + ", true, " + C + ">(a, s); }\n";
+  ni_module *m = new ni_module;
+  const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
+  if (int rc = compile_and_load(src, nvrtc_options, names, m)) {
+    delete m;
+    return rc;
+  }
+  m->kind = NI_KIND_LARGE;
+  m->n = n;
+  m->P = P;
+  m->Q = 0;
+  m->method = method;
+  m->advanced = advanced;
+  m->S = method == NI_RK45 ? 6 : 3;
+  m->block = threads;
+  m->smem = smem;
+  m->large.cpt = 1 << lg;
+  m->large.threads = threads;
+  m->large.smem_bytes = smem;
+  m->large.k_init = m->k_init;
+  m->large.k_run[0] = m->k_run[0];
+  m->large.k_run[1] = m->k_run[1];
   *out = m;
   return NI_OK;
 }
@@ -705,6 +764,12 @@ static bool field_info(ni_ensemble *e, int field, FieldInfo *f) {
 
 NI_API int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr) {
   FieldInfo f;
+  if (e && dptr && field >= NI_F_REC_TRAJ && field <= NI_F_REC_AUX) {
+    if (e->a.rec_cap <= 0) return fail(NI_ERR_INVALID, "recording is not enabled");
+    void *ptrs[] = {e->a.rec_traj, e->a.rec_step, e->a.rec_t, e->a.rec_y, e->a.rec_aux};
+    *dptr = ptrs[field - NI_F_REC_TRAJ];
+    return NI_OK;
+  }
   if (!e || !dptr || !field_info(e, field, &f)) return fail(NI_ERR_INVALID, "bad ensemble / field %d", field);
   *dptr = f.ptr;
   return NI_OK;

@@ -45,6 +45,8 @@
 #define NI_MIN_BLOCKS(n) ((n) <= 3 ? 6 : 1)
 #endif
 
+#define NI_LARGE_MAX_THREADS 512  // CTA-per-trajectory kernels (ni_large.cuh): threads per CTA, x8 components = n <= 4096
+
 #define NI_FLAG_REC_OVERFLOW 1ull
 #define NI_REC_INVALID 0xffffffffu  // rec_traj value of a reserved-but-unused record slot
 

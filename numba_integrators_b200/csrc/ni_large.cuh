@@ -8,7 +8,7 @@
 // stage loop touches HBM: global traffic is y0 in, terminal state out, plus recorded steps.
 //
 // The right-hand side is a 3-point stencil functor
-//     Rhs::eval(t, y_left, y_centre, y_right, p) -> dy_j        (Dirichlet 0 outside 0..n-1)
+//     Rhs::eval(t, y_left, y_centre, y_right, p, j, n) -> dy_j  (Dirichlet 0 outside 0..n-1)
 // so neighbours inside a thread come from registers; only the two edge values per thread go through
 // shared memory (double-buffered: one __syncthreads per RHS evaluation).  The RMS error norm is a
 // warp-shuffle reduction followed by a fixed-order sum of the per-warp partials.
@@ -20,19 +20,18 @@
 #pragma once
 #include "ni_core.cuh"
 
-#define NI_LARGE_MAX_THREADS 512
 
 // p = (k): dy_j = k (y_{j-1} - 2 y_j + y_{j+1})
 struct NiStencilHeat {
   static constexpr int P = 1, Q = 0;
-  NI_DEV static double eval(double, double ym, double yc, double yp, const double *p) {
+  NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
     return __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));
   }
 };
 // p = (nu/dx^2, 1/(2dx)): dy_j = p0 (y_{j-1} - 2 y_j + y_{j+1}) - (y_j p1)(y_{j+1} - y_{j-1})
 struct NiStencilBurgers {
   static constexpr int P = 2, Q = 0;
-  NI_DEV static double eval(double, double ym, double yc, double yp, const double *p) {
+  NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
     const double diff = __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));
     return __dadd_rn(diff, -__dmul_rn(__dmul_rn(yc, p[1]), __dadd_rn(yp, -ym)));
   }
@@ -94,7 +93,7 @@ NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], 
   for (int i = 0; i < CPT; ++i) {
     const double ym = i == 0 ? left : v[i - 1];
     const double yp = i == CPT - 1 ? right : v[i + 1];
-    out[i] = Rhs::eval(t, ym, v[i], yp, p);
+    out[i] = Rhs::eval(t, ym, v[i], yp, p, c.j0 + i, c.n);
   }
   if (!c.full) {
 #pragma unroll

@@ -223,3 +223,40 @@ def test_user_rhs_n8_coupled_oscillators_against_scipy_like_accuracy():
     while ni.step(s2):
         pass
     assert np.array_equal(s2.y, s.y) and np.array_equal(s2.n_accepted, s.n_accepted)
+
+
+def test_record_consumers(tmp_path):
+    """Zero-copy device views of the record log and the npz / parquet writers."""
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(1)
+    y0 = rng.uniform(-1, 1, size=(300, 2))
+    ens = ni.RK45(ni.rhs.harmonic, 0.0, y0, 2.0, rtol=1e-6, atol=1e-6, record=20_000)
+    ens.run()
+    v = ens.record_views()
+    k = v['count']
+    assert v['y'].is_cuda and v['y'].shape == (2, 20_000) and k == ens.n_accepted.sum()
+    t_dev = v['t'][:k].cpu().numpy()
+    rec = ens.record_drain()
+    assert np.array_equal(np.sort(t_dev), np.sort(rec.t))
+    rec.to_npz(tmp_path / 'r.npz')
+    rec.to_parquet(tmp_path / 'r.parquet')
+    z = np.load(tmp_path / 'r.npz')
+    assert np.array_equal(z['y'], rec.y)
+    tab = pq.read_table(tmp_path / 'r.parquet')
+    assert tab.num_rows == len(rec) and tab.column_names == ['traj', 'step', 't', 'y0', 'y1']
+
+
+def test_user_stencil_snippet_matches_builtin_heat():
+    """A user 3-point stencil fused into the CTA-per-trajectory kernels gives the same bits as the built-in."""
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c5_heat(N=6, n=1000, t_bound=2.0)       # ragged: 1000 components on 512 threads x 2
+    user = ni.CudaStencilRHS('return __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));', P=1)
+    a = ni.RK45(user, 0.0, w.y0, 2.0, rtol=1e-8, atol=1e-8, parameters=w.params)
+    b = ni.RK45(ni.rhs.heat1d(w.params[:, 0]), 0.0, w.y0, 2.0, rtol=1e-8, atol=1e-8)
+    a.run()
+    b.run()
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.n_accepted, b.n_accepted)
+    # a space-dependent coefficient uses j and n
+    var = ni.CudaStencilRHS('const double k = p[0] * (1.0 + (double)j / n); return k * (ym - 2.0 * yc + yp);', P=1)
+    c = ni.RK23(var, 0.0, w.y0, 0.5, rtol=1e-6, atol=1e-8, parameters=w.params)
+    assert c.run() == 0 and np.all(np.isfinite(c.y)) and np.all(c.t == 0.5)
