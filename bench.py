@@ -177,6 +177,8 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--arithmetic', default='strict', choices=['strict', 'fast'],
+                    help="'strict' = the reference's unfused FP64 arithmetic (default, bit-faithful); 'fast' = opt-in mode")
     args = ap.parse_args()
     args.traj = args.traj or DEFAULT_TRAJ[args.workload]
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
@@ -204,7 +206,7 @@ def main():
     w = make_workload(args.workload, args.traj, rank, world, args.t_bound)
     N, n = w.N, w.n
     f = ni.BuiltinRHS(w.rhs)
-    ctor_kw = dict(rtol=w.rtol, atol=w.atol, device=local)
+    ctor_kw = dict(rtol=w.rtol, atol=w.atol, device=local, arithmetic=args.arithmetic)
     record = args.workload == 'c2'
     if w.advanced:
         Solver = ni.Advanced(f.P, f.Q, ni.RK45 if w.method == 'RK45' else ni.RK23)
@@ -355,7 +357,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': {'workload': workload_label(w, args.traj), 'parallelism': f'{world} GPU(s), trajectories '
+                'config': {'workload': workload_label(w, args.traj), 'arithmetic': args.arithmetic, 'parallelism': f'{world} GPU(s), trajectories '
                            'sharded by index, no data-path collective',
                            'l2': f'inputs {N * (n + ens.P) * 8 / 1e6:.0f} MB + state per launch exceed the 126 MB L2',
                            'accepted_per_traj': acc_rank / N, 'rejected_per_traj': (att_rank - acc_rank) / N},

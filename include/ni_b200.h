@@ -97,20 +97,23 @@ int ni_device_count(int *count);
 /* ---- modules -------------------------------------------------------------------------
  * Replaces numba's JIT specialisation of the solver on the user's RHS
  * (`nbODEtype`, _aux.py:64-65; `Advanced(parameters_signature, auxiliary_signature, solver)`,
- * _advanced.py:280-368).  `advanced` selects step_advanced semantics (h = h_abs*direction,
- * _advanced.py:163) instead of _step's (h = h_abs, _basic.py:148). */
-int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_module **out);
+ * _advanced.py:280-368).  `mode` is a bit mask: NI_MODE_ADVANCED selects step_advanced semantics
+ * (h = h_abs*direction, _advanced.py:163) instead of _step's (h = h_abs, _basic.py:148). */
+#define NI_MODE_ADVANCED 1 /* step_advanced semantics (h = h_abs*direction), parameters + auxiliary */
+#define NI_MODE_FAST 2     /* opt-in fast arithmetic: contracted multiply-adds, approximate reciprocal and
+                              controller root (agrees with the reference to tolerance, not bit for bit) */
+int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module **out);
 /* `rhs_body` is the body of
  *   __device__ void rhs(double t, const double* y, const double* p, double* dy, double* aux)
  * in CUDA C++; it is fused into the stepper kernels with NVRTC for sm_100a. */
-int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced, const char *nvrtc_options,
+int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int mode, const char *nvrtc_options,
                       ni_module **out);
 /* Large systems (n <= 4096) whose RHS is a 3-point stencil: `stencil_body` is the body of
  *   __device__ double rhs_j(double t, double ym, double yc, double yp, const double* p, int j, int n)
  * returning dy_j from y_{j-1}, y_j, y_{j+1} (zero outside 0..n-1); fused into the CTA-per-trajectory kernels. */
-int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int advanced,
+int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
                               const char *nvrtc_options, ni_module **out);
-int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages);
+int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *mode, int *n_stages);
 /* device layout of the y / klast / aux / params buffers behind ni_ensemble_device_ptr:
  * 0 = component-major [n][N] (thread-per-trajectory kernels), 1 = trajectory-major [N][n] (CTA-per-trajectory) */
 int ni_module_layout(const ni_module *m, int *layout);

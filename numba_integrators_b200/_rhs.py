@@ -27,7 +27,8 @@ class RHS:
     Q = 0
     bound_parameters = None  # parameters closed over (basic API has no `parameters` argument)
 
-    def _module(self, n, method, advanced):
+    def _module(self, n, method, mode):
+        """mode: bit 0 = Advanced semantics, bit 1 = fast arithmetic (include/ni_b200.h NI_MODE_*)."""
         raise NotImplementedError
 
 
@@ -48,9 +49,9 @@ class BuiltinRHS(RHS):
         par = np.stack(cols, axis=-1) if cols else None
         return BuiltinRHS(self.name, par)
 
-    def _module(self, n, method, advanced):
+    def _module(self, n, method, mode):
         out = _lib._vp()
-        _lib.check(_lib.lib().ni_module_builtin(self.rhs_id, int(n), int(method), int(bool(advanced)), out))
+        _lib.check(_lib.lib().ni_module_builtin(self.rhs_id, int(n), int(method), int(mode), out))
         return out
 
     def __repr__(self):
@@ -70,12 +71,12 @@ class CudaRHS(RHS):
         self.nvrtc_options = nvrtc_options
         self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
 
-    def _module(self, n, method, advanced):
+    def _module(self, n, method, mode):
         if n != self.n:
             raise ValueError(f'y0 has {n} components, the RHS was declared with n={self.n}')
         out = _lib._vp()
         _lib.check(_lib.lib().ni_module_compile(self.body.encode(), self.n, self.P, self.Q, int(method),
-                                                int(bool(advanced)), self.nvrtc_options.encode(), out))
+                                                int(mode), self.nvrtc_options.encode(), out))
         return out
 
     def __repr__(self):
@@ -95,10 +96,10 @@ class CudaStencilRHS(RHS):
         self.nvrtc_options = nvrtc_options
         self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
 
-    def _module(self, n, method, advanced):
+    def _module(self, n, method, mode):
         out = _lib._vp()
         _lib.check(_lib.lib().ni_module_compile_stencil(self.body.encode(), int(n), self.P, int(method),
-                                                        int(bool(advanced)), self.nvrtc_options.encode(), out))
+                                                        int(mode), self.nvrtc_options.encode(), out))
         return out
 
     def __repr__(self):

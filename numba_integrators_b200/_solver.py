@@ -118,7 +118,7 @@ class Ensemble:
     """
 
     def __init__(self, fun, t0, y0, t_bound, max_step, rtol, atol, first_step, method, advanced=False,
-                 parameters=None, device=None, record=0, allow_reference_backward_bug=False):
+                 parameters=None, device=None, record=0, allow_reference_backward_bug=False, arithmetic='strict'):
         self._h = None
         self._mod = None
         self._L = _lib.lib()
@@ -162,7 +162,12 @@ class Ensemble:
             device = int(os.environ.get('LOCAL_RANK', '0'))
         self.device = int(device)
 
-        self._mod = self.fun._module(self.n, method, self._advanced)
+        if arithmetic not in ('strict', 'fast'):
+            raise ValueError("arithmetic must be 'strict' (the reference's unfused FP64 arithmetic, bit-faithful) or "
+                             "'fast' (contracted multiply-adds, approximate reciprocal / controller root)")
+        self.arithmetic = arithmetic
+        self._mod = self.fun._module(self.n, method, (_lib.MODE_ADVANCED if self._advanced else 0)
+                                     | (_lib.MODE_FAST if arithmetic == 'fast' else 0))
         kind = C.c_int(0)
         check(self._L.ni_module_layout(self._mod, kind))
         self.kind = kind.value  # 0: component-major device buffers, 1: trajectory-major

@@ -58,7 +58,7 @@ NI_API int ni_device_count(int *count) {
 // ------------------------------------------------------------------ modules
 struct ni_module {
   int kind = NI_KIND_SMALL;
-  int n = 0, P = 0, Q = 0, method = NI_RK45, advanced = 0, S = 6;
+  int n = 0, P = 0, Q = 0, method = NI_RK45, advanced = 0, fast = 0, S = 6;
   const void *k_init = nullptr;
   const void *k_run[2] = {nullptr, nullptr};  // [record]
   int block = NI_BLOCK;
@@ -81,15 +81,17 @@ static const NiKernelSet *builtin_small(int rhs_id, int n) {
   }
 }
 
-NI_API int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_module **out) {
+NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
   if (n < 1) return fail(NI_ERR_INVALID, "n must be >= 1");
-  advanced = advanced ? 1 : 0;
+  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
+  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0;
   ni_module *m = new ni_module;
   m->method = method;
   m->advanced = advanced;
+  m->fast = fast;
   m->S = method == NI_RK45 ? 6 : 3;
   if (const NiKernelSet *ks = builtin_small(rhs_id, n)) {
     m->kind = NI_KIND_SMALL;
@@ -97,10 +99,14 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int advanced, ni_mod
     m->P = ks->P;
     m->Q = ks->Q;
     m->k_init = ks->init[method];
-    m->k_run[0] = ks->run[method][advanced][0];
-    m->k_run[1] = ks->run[method][advanced][1];
+    m->k_run[0] = ks->run[method][advanced][0][fast];
+    m->k_run[1] = ks->run[method][advanced][1][fast];
     *out = m;
     return NI_OK;
+  }
+  if (fast && (rhs_id == NI_RHS_HEAT1D || rhs_id == NI_RHS_BURGERS1D)) {
+    delete m;
+    return fail(NI_ERR_UNSUPPORTED, "NI_MODE_FAST is implemented for the thread-per-trajectory kernels only");
   }
   if (ni_large_builtin(rhs_id, n, method, advanced, &m->large, &m->P, &m->Q)) {
     m->kind = NI_KIND_LARGE;
@@ -169,8 +175,7 @@ static int compile_and_load(const std::string &src, const char *nvrtc_options, c
   const char *hdr_name[] = {"ni_core.cuh", "ni_math.cuh", "ni_large.cuh"};
   int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 3, hdr_src, hdr_name);
   if (rc) return fail(NI_ERR_NVRTC, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(rc));
-  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo",
-                                   "-default-device"};
+  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
   if (nvrtc_options && *nvrtc_options) {  // space separated extra options
     std::string o(nvrtc_options);
     size_t pos = 0;
@@ -215,7 +220,7 @@ static int compile_and_load(const std::string &src, const char *nvrtc_options, c
   return NI_OK;
 }
 
-NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int advanced,
+NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int mode,
                              const char *nvrtc_options, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -225,28 +230,34 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   if (n > NI_MAX_SMALL_N)
     return fail(NI_ERR_UNSUPPORTED, "dense user RHS snippets support n <= %d (got %d); larger systems must be "
                 "3-point stencils (ni_module_compile_stencil)", NI_MAX_SMALL_N, n);
-  advanced = advanced ? 1 : 0;
+  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
+  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0;
   std::string src;
   src += "#include \"ni_core.cuh\"\n";
   src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
          ", Q = " + std::to_string(Q) + ";\n";
+  src += "  template <bool FAST>\n";
   src += "  NI_DEV static void eval(double t, const double* y, const double* p, double* dy, double* aux) {\n";
   src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
   src += rhs_body;
   src += "\n  }\n};\n";
-  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false";
+  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false",
+                    F = fast ? "true" : "false";
   src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
          "ni_small_init_body<NiUserRhs, " + M + ">(a); }\n";
   src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run(const NiArgs a) { "
-         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false>(a); }\n";
+         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false, " + F + ">(a); }\n";
   src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
-         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true>(a); }\n";
+         "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true, " + F + ">(a); }\n";
   ni_module *m = new ni_module;
   const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
-  if (int rc = compile_and_load(src, nvrtc_options, names, m)) {
+  // strict: the snippet's own a*b+c must not be contracted either; fast: let NVRTC contract it
+  const std::string all_opts = std::string(fast ? "--fmad=true " : "--fmad=false ") + (nvrtc_options ? nvrtc_options : "");
+  if (int rc = compile_and_load(src, all_opts.c_str(), names, m)) {
     delete m;
     return rc;
   }
+  m->fast = fast;
   m->kind = NI_KIND_SMALL;
   m->n = n;
   m->P = P;
@@ -258,7 +269,7 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   return NI_OK;
 }
 
-NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int advanced,
+NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
                                      const char *nvrtc_options, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -269,7 +280,8 @@ NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int
   size_t smem = 0;
   if (!ni_large_dims(n, method, &lg, &threads, &smem))
     return fail(NI_ERR_UNSUPPORTED, "stencil systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_THREADS * 8, n);
-  advanced = advanced ? 1 : 0;
+  if (mode & ~NI_MODE_ADVANCED) return fail(NI_ERR_UNSUPPORTED, "stencil kernels support NI_MODE_ADVANCED only");
+  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0;
   const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false",
                     C = std::to_string(1 << lg);
   std::string src;
@@ -288,7 +300,8 @@ NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int
          ", " + A + ", true, " + C + ">(a, s); }\n";
   ni_module *m = new ni_module;
   const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
-  if (int rc = compile_and_load(src, nvrtc_options, names, m)) {
+  const std::string all_opts = std::string("--fmad=false ") + (nvrtc_options ? nvrtc_options : "");
+  if (int rc = compile_and_load(src, all_opts.c_str(), names, m)) {
     delete m;
     return rc;
   }
@@ -317,7 +330,7 @@ NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *metho
   if (P) *P = m->P;
   if (Q) *Q = m->Q;
   if (method) *method = m->method;
-  if (advanced) *advanced = m->advanced;
+  if (advanced) *advanced = m->advanced | (m->fast ? NI_MODE_FAST : 0);
   if (n_stages) *n_stages = m->S;
   return NI_OK;
 }

@@ -89,6 +89,34 @@ struct NiArgs {
   unsigned char *cond_hit;
 };
 
+// Arithmetic policy.  Strict (FAST = false): every element-wise expression is evaluated unfused, as numba
+// evaluates it in the reference (bit-identical results).  Fast: multiply-adds are
+// contracted; agreement with the reference is then to tolerance only.
+template <bool FAST>
+struct NiA {
+  NI_DEV static double mul(double a, double b) { return __dmul_rn(a, b); }
+  NI_DEV static double add(double a, double b) { return __dadd_rn(a, b); }
+  NI_DEV static double sub(double a, double b) { return __dadd_rn(a, -b); }
+  NI_DEV static double madd(double a, double b, double c) {  // a*b + c
+    if constexpr (FAST)
+      return fma(a, b, c);
+    else
+      return __dadd_rn(__dmul_rn(a, b), c);
+  }
+  NI_DEV static double msub(double a, double b, double c) {  // a*b - c
+    if constexpr (FAST)
+      return fma(a, b, -c);
+    else
+      return __dadd_rn(__dmul_rn(a, b), -c);
+  }
+  NI_DEV static double nmadd(double a, double b, double c) {  // c - a*b
+    if constexpr (FAST)
+      return fma(-a, b, c);
+    else
+      return __dadd_rn(c, -__dmul_rn(a, b));
+  }
+};
+
 // ---------------------------------------------------------------- utilities
 template <int I>
 struct NiInt {
@@ -345,7 +373,7 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
 #pragma unroll
     for (int i = 0; i < P; ++i) p[i] = a.params_rows[idx * P + i];
     const double t0 = a.t0[idx * a.t0_stride], tb = a.tb0[idx * a.tb_stride];
-    Rhs::eval(t0, y, p, f0, aux);
+    Rhs::template eval<false>(t0, y, p, f0, aux);
     const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
     double h_abs;
     if (a.first_step == 0.0) {
@@ -363,7 +391,7 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
       double y1[n], f1[n], auxd[Q > 0 ? Q : 1];
 #pragma unroll
       for (int i = 0; i < n; ++i) y1[i] = fma(hd, f0[i], y[i]);
-      Rhs::eval(__dadd_rn(t0, hd), y1, p, f1, auxd);
+      Rhs::template eval<false>(__dadd_rn(t0, hd), y1, p, f1, auxd);
 #pragma unroll
       for (int i = 0; i < n; ++i) tmp[i] = __dadd_rn(f1[i], -f0[i]) / scale[i];
       const double d2 = ni_rms<n>(tmp) / h0;
@@ -403,7 +431,7 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
 // diverges inside the stage loop).  A lane retires its trajectory when it finished, failed,
 // used up max_accepts / max_attempts, hit the ff2cond predicate or found the record log full;
 // it then pulls the next trajectory index from the queue.
-template <class Rhs, int METHOD, bool ADV, bool REC>
+template <class Rhs, int METHOD, bool ADV, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
   using Tab = NiTab<METHOD>;
@@ -521,22 +549,35 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         double d[n], ys[n], auxd[Q > 0 ? Q : 1];
         ni_dot<METHOD, s, s, n>(K, d);
 #pragma unroll
-        for (int i = 0; i < n; ++i) ys[i] = __dadd_rn(y[i], __dmul_rn(d[i], h));
-        Rhs::eval(__dadd_rn(t, __dmul_rn(ni_cval<METHOD, 0, s>(), h)), ys, p, K[s], auxd);
+        for (int i = 0; i < n; ++i) ys[i] = NiA<FAST>::madd(d[i], h, y[i]);
+        Rhs::template eval<FAST>(NiA<FAST>::madd(ni_cval<METHOD, 0, s>(), h, t), ys, p, K[s], auxd);
       });
       double d[n];
       ni_dot<METHOD, S, S, n>(K, d);
 #pragma unroll
-      for (int i = 0; i < n; ++i) yn[i] = __dadd_rn(y[i], __dmul_rn(h, d[i]));
-      Rhs::eval(tn, yn, p, K[S], auxn);
+      for (int i = 0; i < n; ++i) yn[i] = NiA<FAST>::madd(h, d[i], y[i]);
+      Rhs::template eval<FAST>(tn, yn, p, K[S], auxn);
       double ev[n];
       ni_dot<METHOD, S + 1, S + 1, n>(K, ev);
+      if constexpr (FAST) {
+        // mean square error instead of the RMS norm: the controller takes (en^2)^(-1/(2K)) (ni_pow_fast)
+        double msq = 0.0;
 #pragma unroll
-      for (int i = 0; i < n; ++i) {
-        ev[i] = __dmul_rn(ev[i], h) / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
-        kn[i] = K[S][i];
+        for (int i = 0; i < n; ++i) {
+          const double sc = fma(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i], a.atol[i]);
+          const double e = __dmul_rn(ev[i], __dmul_rn(h, ni_rcp_fast(sc)));
+          msq = fma(e, e, msq);
+          kn[i] = K[S][i];
+        }
+        en = __dmul_rn(msq, 1.0 / n);  // en holds error_norm**2 in fast mode (same < 1, == 0, NaN tests)
+      } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          ev[i] = __dmul_rn(ev[i], h) / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+          kn[i] = K[S][i];
+        }
+        en = ni_rms<n>(ev);
       }
-      en = ni_rms<n>(ev);
       ok = en < 1.0;
       --att_left;
     }
@@ -579,7 +620,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       const bool park = REC && ok && slot >= a.rec_cap;  // log full: undo this attempt (state before an
                                                          // attempt is exactly t, y, h_abs, K[-1])
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
-      const double sp = __dmul_rn(0.9, ni_pow_ctrl<Tab::ORDER + 1>(en));
+      const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
       const double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
       const double h_new = __dmul_rn(h_abs, fac);
       const bool fail = !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
@@ -641,7 +682,7 @@ template <class Rhs, int METHOD>
 __global__ void __launch_bounds__(NI_BLOCK) ni_k_init(const NiArgs a) {
   ni_small_init_body<Rhs, METHOD>(a);
 }
-template <class Rhs, int METHOD, bool ADV, bool REC>
+template <class Rhs, int METHOD, bool ADV, bool REC, bool FAST>
 __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(Rhs::N)) ni_k_run(const NiArgs a) {
-  ni_small_run_body<Rhs, METHOD, ADV, REC>(a);
+  ni_small_run_body<Rhs, METHOD, ADV, REC, FAST>(a);
 }

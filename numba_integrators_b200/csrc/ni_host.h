@@ -8,31 +8,28 @@
 
 struct NiKernelSet {
   int kind;
-  int n, P, Q;               // n < 0: any dimension (large kernels take n at run time)
-  const void *init[2];       // [method]
-  const void *run[2][2][2];  // [method][advanced][record]
+  int n, P, Q;                  // n < 0: any dimension (large kernels take n at run time)
+  const void *init[2];          // [method]
+  const void *run[2][2][2][2];  // [method][advanced][record][fast arithmetic]
 };
 
 #define NI_VISIBLE_INTERNAL __attribute__((visibility("hidden")))
 
-// Fills a kernel set with every (method, advanced, record) instantiation for an RHS functor.
-#define NI_DEFINE_SMALL_KSET(FN, RHS)                                                            \
-  NI_VISIBLE_INTERNAL const NiKernelSet *FN() {                                                  \
-    static const NiKernelSet ks = {                                                              \
-        NI_KIND_SMALL,                                                                           \
-        RHS::N,                                                                                  \
-        RHS::P,                                                                                  \
-        RHS::Q,                                                                                  \
-        {(const void *)&ni_k_init<RHS, NI_RK23>, (const void *)&ni_k_init<RHS, NI_RK45>},        \
-        {{{(const void *)&ni_k_run<RHS, NI_RK23, false, false>,                                  \
-           (const void *)&ni_k_run<RHS, NI_RK23, false, true>},                                  \
-          {(const void *)&ni_k_run<RHS, NI_RK23, true, false>,                                   \
-           (const void *)&ni_k_run<RHS, NI_RK23, true, true>}},                                  \
-         {{(const void *)&ni_k_run<RHS, NI_RK45, false, false>,                                  \
-           (const void *)&ni_k_run<RHS, NI_RK45, false, true>},                                  \
-          {(const void *)&ni_k_run<RHS, NI_RK45, true, false>,                                   \
-           (const void *)&ni_k_run<RHS, NI_RK45, true, true>}}}};                                \
-    return &ks;                                                                                  \
+#define NI_KR(RHS, M, A, R) {(const void *)&ni_k_run<RHS, M, A, R, false>, (const void *)&ni_k_run<RHS, M, A, R, true>}
+// Fills a kernel set with every (method, advanced, record, arithmetic) instantiation for an RHS functor.
+#define NI_DEFINE_SMALL_KSET(FN, RHS)                                                         \
+  NI_VISIBLE_INTERNAL const NiKernelSet *FN() {                                               \
+    static const NiKernelSet ks = {                                                           \
+        NI_KIND_SMALL,                                                                        \
+        RHS::N,                                                                               \
+        RHS::P,                                                                               \
+        RHS::Q,                                                                               \
+        {(const void *)&ni_k_init<RHS, NI_RK23>, (const void *)&ni_k_init<RHS, NI_RK45>},     \
+        {{{NI_KR(RHS, NI_RK23, false, false), NI_KR(RHS, NI_RK23, false, true)},              \
+          {NI_KR(RHS, NI_RK23, true, false), NI_KR(RHS, NI_RK23, true, true)}},               \
+         {{NI_KR(RHS, NI_RK45, false, false), NI_KR(RHS, NI_RK45, false, true)},              \
+          {NI_KR(RHS, NI_RK45, true, false), NI_KR(RHS, NI_RK45, true, true)}}}};             \
+    return &ks;                                                                               \
   }
 
 const NiKernelSet *ni_kset_harmonic();

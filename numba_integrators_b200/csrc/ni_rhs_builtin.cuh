@@ -19,13 +19,12 @@
 #define NI_RHS_BLOWUP 8
 #define NI_RHS_COUNT 9
 
-#define NI_SUB(a, b) __dadd_rn((a), -(b))
-#define NI_ADD(a, b) __dadd_rn((a), (b))
-#define NI_MUL(a, b) __dmul_rn((a), (b))
+// A = NiA<FAST>: strict (unfused, the reference's arithmetic) or fast (contracted multiply-adds)
 
 // y0' = y1, y1' = -y0   (reference.py:46-49 "sine", README.md:54-57)
 struct NiRhsHarmonic {
   static constexpr int N = 2, P = 0, Q = 0;
+  template <bool FAST>
   NI_DEV static void eval(double, const double *y, const double *, double *dy, double *) {
     dy[0] = y[1];
     dy[1] = -y[0];
@@ -35,21 +34,25 @@ struct NiRhsHarmonic {
 // Lorenz-63, p = (sigma, rho, beta), aux = x^2 + y^2 + z^2
 struct NiRhsLorenz63 {
   static constexpr int N = 3, P = 3, Q = 1;
+  template <bool FAST>
   NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *aux) {
+    using A = NiA<FAST>;
     const double x = y[0], yy = y[1], z = y[2];
-    dy[0] = NI_MUL(p[0], NI_SUB(yy, x));
-    dy[1] = NI_SUB(NI_MUL(x, NI_SUB(p[1], z)), yy);
-    dy[2] = NI_SUB(NI_MUL(x, yy), NI_MUL(p[2], z));
-    aux[0] = NI_ADD(NI_ADD(NI_MUL(x, x), NI_MUL(yy, yy)), NI_MUL(z, z));
+    dy[0] = A::mul(p[0], A::sub(yy, x));
+    dy[1] = A::msub(x, A::sub(p[1], z), yy);
+    dy[2] = A::msub(x, yy, A::mul(p[2], z));
+    aux[0] = A::madd(z, z, A::madd(yy, yy, A::mul(x, x)));  // strict: (x*x + y*y) + z*z
   }
 };
 
 // Van der Pol, p = (mu)
 struct NiRhsVanDerPol {
   static constexpr int N = 2, P = 1, Q = 0;
+  template <bool FAST>
   NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *) {
+    using A = NiA<FAST>;
     dy[0] = y[1];
-    dy[1] = NI_SUB(NI_MUL(NI_MUL(p[0], NI_SUB(1.0, NI_MUL(y[0], y[0]))), y[1]), y[0]);
+    dy[1] = A::msub(A::mul(p[0], A::nmadd(y[0], y[0], 1.0)), y[1], y[0]);  // (mu (1 - y0^2)) y1 - y0
   }
 };
 
@@ -57,6 +60,7 @@ struct NiRhsVanDerPol {
 template <int N_>
 struct NiRhsExponential {
   static constexpr int N = N_, P = 0, Q = 0;
+  template <bool FAST>
   NI_DEV static void eval(double, const double *y, const double *, double *dy, double *) {
 #pragma unroll
     for (int i = 0; i < N; ++i) dy[i] = y[i];
@@ -66,18 +70,22 @@ struct NiRhsExponential {
 // y' = 2y/x - x^2 y^2   (reference.py:38-41)
 struct NiRhsRiccati {
   static constexpr int N = 1, P = 0, Q = 0;
+  template <bool FAST>
   NI_DEV static void eval(double t, const double *y, const double *, double *dy, double *) {
-    dy[0] = NI_SUB(NI_MUL(2.0, y[0]) / t, NI_MUL(NI_MUL(t, t), NI_MUL(y[0], y[0])));
+    using A = NiA<FAST>;
+    dy[0] = A::nmadd(A::mul(t, t), A::mul(y[0], y[0]), A::mul(2.0, y[0]) / t);
   }
 };
 
 // README.md:80-85 Advanced example: p = (a, b0, b1); aux = a*y1; dy = (aux + b0, -y0 + b1)
 struct NiRhsReadmeAdvanced {
   static constexpr int N = 2, P = 3, Q = 1;
+  template <bool FAST>
   NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *aux) {
-    const double a = NI_MUL(p[0], y[1]);
-    dy[0] = NI_ADD(a, p[1]);
-    dy[1] = NI_ADD(-y[0], p[2]);
+    using A = NiA<FAST>;
+    const double a = A::mul(p[0], y[1]);
+    dy[0] = A::add(a, p[1]);
+    dy[1] = A::add(-y[0], p[2]);
     aux[0] = a;
   }
 };
@@ -85,21 +93,8 @@ struct NiRhsReadmeAdvanced {
 // y' = y^2 (finite-time blow-up: exercises the step-too-small exit, _basic.py:179-180)
 struct NiRhsBlowup {
   static constexpr int N = 1, P = 0, Q = 0;
+  template <bool FAST>
   NI_DEV static void eval(double, const double *y, const double *, double *dy, double *) {
-    dy[0] = NI_MUL(y[0], y[0]);
-  }
-};
-
-// Small method-of-lines heat / Burgers systems (N <= NI_MAX_SMALL_N) in registers; the
-// large-dimension versions live in ni_large.cuh.
-template <int N_>
-struct NiRhsHeatSmall {
-  static constexpr int N = N_, P = 1, Q = 0;
-  NI_DEV static void eval(double, const double *y, const double *p, double *dy, double *) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const double ym = j > 0 ? y[j - 1] : 0.0, yp = j + 1 < N ? y[j + 1] : 0.0;
-      dy[j] = NI_MUL(p[0], NI_ADD(NI_SUB(ym, NI_MUL(2.0, y[j])), yp));
-    }
+    dy[0] = NiA<FAST>::mul(y[0], y[0]);
   }
 };

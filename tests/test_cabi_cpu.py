@@ -57,6 +57,12 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.ni_module_info(m, *vals) == 0
     assert [v.value for v in vals] == [3, 3, 1, 1, 1, 6]
     assert L.ni_module_destroy(m) == 0
+    assert L.ni_module_builtin(1, 3, 1, 3, m) == 0  # + NI_MODE_FAST
+    assert L.ni_module_info(m, *vals) == 0 and vals[4].value == 3
+    assert L.ni_module_destroy(m) == 0
+    assert L.ni_module_builtin(3, 64, 1, 2, m) == _lib.NI_ERR_UNSUPPORTED  # no fast mode for the stencil kernels
+    assert L.ni_module_builtin(1, 3, 1, 8, m) == _lib.NI_ERR_INVALID
+    assert L.ni_module_destroy(m) == 0
 
 
 def test_product_package_never_touches_the_oracle():

@@ -120,3 +120,29 @@ def test_parity_against_oracle_on_larger_samples(cfg, oracle):
     assert same.mean() >= 0.999, same.mean()
     assert np.mean(rel <= 1e-12) >= need, (np.mean(rel <= 1e-12), rel.max())
     assert np.all(s.t == w.t_bound) and np.all(s.status == 1)
+
+
+@pytest.mark.parametrize('cfg', ['c2', 'c3_t1', 'c4_tol1e-8'])
+def test_fast_arithmetic_mode_meets_the_tolerance_bar(cfg, oracle):
+    """arithmetic='fast' (contracted multiply-adds, approximate reciprocal, root of the mean-square error) is
+    not bit-faithful; it must still meet the north-star bar: <= 1e-12 relative and identical accepted /
+    rejected counts on >= 99.9 % of trajectories at the parity horizons (C4: the appendix-C floor, 97 %)."""
+    w = {'c2': wl.c2_harmonic(N=8192), 'c3_t1': wl.c3_lorenz(N=16384, t_bound=1.0),
+         'c4_tol1e-8': wl.c4_vanderpol(N=2048, tol=1e-8)}[cfg]
+    m = oracle.RK45 if w.method == 'RK45' else oracle.RK23
+    ref = oracle.run_ensemble(w.rhs, m, w.t0, w.y0, w.t_bound, params=w.params, rtol=w.rtol, atol=w.atol,
+                              advanced=w.advanced)
+    f = ni.BuiltinRHS(w.rhs)
+    kw = dict(rtol=w.rtol, atol=w.atol, arithmetic='fast')
+    if w.advanced:
+        s = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, w.y0, w.params, w.t_bound, **kw)
+    else:
+        ctor = ni.RK45 if w.method == 'RK45' else ni.RK23
+        s = ctor(f(*w.params.T) if f.P else f, w.t0, w.y0, w.t_bound, **kw)
+    assert s.run() == 0
+    rel = np.max(np.abs(s.y - ref['y']), axis=1) / np.max(np.abs(ref['y']), axis=1)
+    same = (s.n_accepted == ref['n_accepted']) & (s.n_rejected == ref['n_rejected'])
+    need = {'c2': 0.999, 'c3_t1': 0.999, 'c4_tol1e-8': 0.97}[cfg]
+    assert same.mean() >= 0.999, same.mean()
+    assert np.mean(rel <= 1e-12) >= need, (np.mean(rel <= 1e-12), rel.max())
+    assert np.all(s.t == w.t_bound) and np.all(s.status == 1)

@@ -23,6 +23,9 @@ extern "C" {
 double pow5(double x) { return ni_pow_ctrl<5>(x); }
 double pow3(double x) { return ni_pow_ctrl<3>(x); }
 double div3(double x) { return ni_div3(x); }
+double powf10(double x) { return ni_pow_fast<10>(x); }
+double powf6(double x) { return ni_pow_fast<6>(x); }
+double rcpf(double x) { return ni_rcp_fast(x); }
 double libm_pow(double x, double e) { return std::pow(x, e); }
 void div3_check(const double* a, long n, long* bad) { long b = 0; for (long i = 0; i < n; ++i) b += (ni_div3(a[i]) != a[i] / 3.0); *bad = b; }
 }
@@ -36,7 +39,7 @@ def build():
     subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-mfma', '-shared', '-fPIC', '-I',
                     str(ROOT / 'numba_integrators_b200' / 'csrc'), str(d / 't.cpp'), '-o', str(so)], check=True)
     L = ctypes.CDLL(str(so))
-    for f in ('pow5', 'pow3', 'div3'):
+    for f in ('pow5', 'pow3', 'div3', 'powf10', 'powf6', 'rcpf'):
         getattr(L, f).restype = ctypes.c_double
         getattr(L, f).argtypes = [ctypes.c_double]
     L.libm_pow.restype = ctypes.c_double
@@ -69,6 +72,13 @@ def main(n=20000):
     L.div3_check(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(a), ctypes.byref(bad))
     print(f'ni_div3 != a/3.0 on {bad.value} of {len(a)} samples')
     res['div3'] = bad.value
+    # fast-mode helpers: relative error of the controller root on en**2 and of the reciprocal
+    xs = 10.0 ** rng.uniform(-12, 6, 20000)
+    e10 = max(abs(L.powf10(float(x)) / float(x) ** -0.1 - 1) for x in xs)
+    e6 = max(abs(L.powf6(float(x)) / float(x) ** (-1 / 6) - 1) for x in xs)
+    er = max(abs(L.rcpf(float(x)) * float(x) - 1) for x in xs)
+    print(f'fast mode: max rel error  x**-0.1: {e10:.2e}   x**-1/6: {e6:.2e}   1/x: {er:.2e}')
+    res['fast'] = (e10, e6, er)
     return res
 
 
