@@ -191,6 +191,9 @@ def main():
     import torch
     import torch.distributed as dist
 
+    from numba_integrators_b200 import build as _build
+    if not _build.LIB.exists() and rank == 0:
+        _build.build()  # build artefacts are git-ignored; normally they travel with the snapshot
     import numba_integrators_b200 as ni
     from numba_integrators_b200 import _lib
 

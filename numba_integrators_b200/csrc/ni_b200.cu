@@ -279,7 +279,7 @@ NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int
   int lg = 0, threads = 0;
   size_t smem = 0;
   if (!ni_large_dims(n, method, &lg, &threads, &smem))
-    return fail(NI_ERR_UNSUPPORTED, "stencil systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_THREADS * 8, n);
+    return fail(NI_ERR_UNSUPPORTED, "stencil systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_N, n);
   if (mode & ~NI_MODE_ADVANCED) return fail(NI_ERR_UNSUPPORTED, "stencil kernels support NI_MODE_ADVANCED only");
   const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0;
   const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false",

@@ -45,7 +45,10 @@
 #define NI_MIN_BLOCKS(n) ((n) <= 3 ? 6 : 1)
 #endif
 
-#define NI_LARGE_MAX_THREADS 512  // CTA-per-trajectory kernels (ni_large.cuh): threads per CTA, x8 components = n <= 4096
+#ifndef NI_LARGE_MAX_THREADS
+#define NI_LARGE_MAX_THREADS 512  // CTA-per-trajectory kernels (ni_large.cuh): threads per CTA
+#endif
+#define NI_LARGE_MAX_N 4096  // largest state dimension of the CTA-per-trajectory kernels
 
 #define NI_FLAG_REC_OVERFLOW 1ull
 #define NI_REC_INVALID 0xffffffffu  // rec_traj value of a reserved-but-unused record slot

@@ -6,7 +6,7 @@
 #include "ni_rhs_builtin.cuh"
 
 NI_VISIBLE_INTERNAL bool ni_large_dims(int n, int method, int *lg_out, int *threads, size_t *smem_bytes) {
-  if (n < 1 || n > NI_LARGE_MAX_THREADS * 8) return false;
+  if (n < 1 || n > NI_LARGE_MAX_N) return false;
   int lg = 0;  // components per thread = 1 << lg: the smallest that fits NI_LARGE_MAX_THREADS threads
   while ((n + (1 << lg) - 1) / (1 << lg) > NI_LARGE_MAX_THREADS) ++lg;
   const int cpt = 1 << lg;

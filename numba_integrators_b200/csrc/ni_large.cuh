@@ -37,30 +37,32 @@ struct NiStencilBurgers {
   }
 };
 
-// Which stage vectors stay in registers: K0 always (read by every stage), K2 for RK45 (5 reads).
+// Which stage vectors stay in registers: K0 always (read by every stage); K2 for RK45 (5 reads) when the CTA has
+// 512 threads x 128 registers.  With 1024 threads x 64 registers only K0 fits.
+#ifndef NI_LARGE_K2_IN_REG
+#define NI_LARGE_K2_IN_REG (NI_LARGE_MAX_THREADS <= 512)
+#endif
 template <int METHOD, int J>
 struct NiKInReg {
-  static constexpr bool value = (J == 0) || (METHOD == NI_RK45 && J == 2);
+  static constexpr bool value = (J == 0) || (NI_LARGE_K2_IN_REG && METHOD == NI_RK45 && J == 2);
 };
-// shared-memory slot of stage vector J (J = S is the new FSAL stage), slot count, and the slot of y_new
+// shared-memory slot of stage vector J (1..S; J = S is the new FSAL stage) and the slot count
 template <int METHOD>
-struct NiLargeSlots;
-template <>
-struct NiLargeSlots<NI_RK45> {  // K1 K3 K4 K5 K6 | y_new
-  NI_HD static constexpr int slot(int j) { return j == 1 ? 0 : j - 2; }
-  static constexpr int KSLOTS = 5, TOTAL = 6;
-};
-template <>
-struct NiLargeSlots<NI_RK23> {  // K1 K2 K3 | y_new
-  NI_HD static constexpr int slot(int j) { return j - 1; }
-  static constexpr int KSLOTS = 3, TOTAL = 4;
+struct NiLargeSlots {
+  NI_HD static constexpr int slot(int j) {
+    int s = 0;
+    for (int k = 1; k < j; ++k) s += (NI_LARGE_K2_IN_REG && METHOD == NI_RK45 && k == 2) ? 0 : 1;
+    return s;
+  }
+  static constexpr int KSLOTS = slot(NiTab<METHOD>::S) + 1, TOTAL = KSLOTS;
 };
 
 // dynamic shared memory of one CTA, in doubles.  Stage vectors are laid out [slot][component][NI_LARGE_MAX_THREADS]
 // whatever the CTA size, so that every access is `thread base + immediate offset`.
 NI_HD constexpr size_t ni_large_smem_doubles(int method, int threads, int cpt) {
   (void)threads;
-  return (size_t)(method == NI_RK45 ? 6 : 4) * NI_LARGE_MAX_THREADS * cpt + 4 * (size_t)NI_LARGE_MAX_THREADS + 2 * 32 + 8;
+  return (size_t)(method == NI_RK45 ? NiLargeSlots<NI_RK45>::TOTAL : NiLargeSlots<NI_RK23>::TOTAL) *
+             NI_LARGE_MAX_THREADS * cpt + 4 * (size_t)NI_LARGE_MAX_THREADS + 2 * 32 + 8;
 }
 
 struct NiLargeCtx {
@@ -223,7 +225,6 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
   // shared stage vector J, component i of this thread
   double *const svb = c.vec + tid;
   auto sv = [&](int slot, int i) -> double & { return svb[(slot * CPT + i) * NI_LARGE_MAX_THREADS]; };
-  constexpr int YN_SLOT = Slots::KSLOTS;
 
   for (;;) {
     // ---- next trajectory (one queue pop per CTA)

@@ -13,6 +13,10 @@ GOLDEN = ROOT / 'tests' / 'golden'
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    # the CUDA extension and the CPU oracle are build artefacts (git-ignored): compile them when absent
+    from numba_integrators_b200 import build as _b
+    if not _b.LIB.exists():
+        _b.build()
 
 
 def golden_names():
