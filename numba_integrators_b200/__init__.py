@@ -11,11 +11,12 @@ __version__ = '0.1.0'
 
 from . import _rhs as rhs
 from ._lib import NiError
-from ._rhs import BuiltinRHS, CudaRHS, CudaStencilRHS
+from ._rhs import BuiltinRHS, CudaRHS, CudaStencilRHS, PythonRHS
+from ._translate import TranslationError, translate
 from ._solver import (ALL, MAX_FACTOR, MIN_FACTOR, RK, RK23, RK45, SAFETY, Advanced, Condition, Ensemble, Records,
                       Solver, Solvers, StepMask, aux_above, aux_below, convert, ff2cond, ff2t, step, y_above,
                       y_below)
 
-__all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaRHS', 'CudaStencilRHS', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
+__all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaRHS', 'CudaStencilRHS', 'PythonRHS', 'TranslationError', 'translate', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
            'Records', 'Solver', 'Solvers', 'StepMask', 'aux_above', 'aux_below', 'convert', 'ff2cond', 'ff2t', 'rhs',
            'step', 'y_above', 'y_below', 'SAFETY', 'MIN_FACTOR', 'MAX_FACTOR']

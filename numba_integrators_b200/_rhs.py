@@ -118,11 +118,34 @@ readme_advanced = BuiltinRHS('readme_advanced')
 blowup = BuiltinRHS('blowup')
 
 
+class PythonRHS(RHS):
+    """A reference-style Python / numba right-hand side `f(t, y)` or `f(t, y, parameters) -> (dy, aux)`.
+    Its source is translated to a CUDA C++ snippet (numba_integrators_b200/_translate.py) once the state
+    dimension and the parameter layout are known; the Python function itself is never executed."""
+
+    def __init__(self, fun):
+        self.fun = fun
+        self.name = getattr(getattr(fun, 'py_func', fun), '__name__', 'python_rhs')
+        self.n = None
+
+    def specialise(self, n, parameters, advanced):
+        from ._translate import translate
+        body, P, Q, aux_scalar = translate(self.fun, n, parameters, advanced)
+        rhs = CudaRHS(body, n=n, P=P, Q=Q, name=self.name)
+        rhs.aux_scalar = aux_scalar
+        rhs.python_source = self.fun
+        return rhs
+
+    def __repr__(self):
+        return f'PythonRHS({self.name})'
+
+
 def as_rhs(f) -> RHS:
     if isinstance(f, RHS):
         return f
     if isinstance(f, str):
         return BuiltinRHS(f)
-    raise TypeError('the right-hand side must be a built-in name / ni.rhs.* object or a ni.CudaRHS snippet; '
-                    'Python / numba callables cannot be fused into the CUDA kernels '
-                    f'(got {type(f).__name__})')
+    if callable(f):
+        return PythonRHS(f)
+    raise TypeError('the right-hand side must be a built-in name / ni.rhs.* object, a ni.CudaRHS / '
+                    f'ni.CudaStencilRHS snippet or a Python function (got {type(f).__name__})')

@@ -22,7 +22,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check
-from ._rhs import RHS, as_rhs
+from ._rhs import RHS, PythonRHS, as_rhs
 
 SAFETY = 0.9       # _aux.py:16
 MIN_FACTOR = 0.2   # _aux.py:18
@@ -143,6 +143,8 @@ class Ensemble:
         if not self._advanced and not allow_reference_backward_bug and np.any(tba < t0a):
             raise ValueError('the basic RK23/RK45 ignore `direction` when forming the step (_basic.py:148) and '
                              'never reach a t_bound < t0; build the solver through ni.Advanced for backward runs')
+        if isinstance(self.fun, PythonRHS):  # translate the Python source into a CUDA snippet (never executed)
+            self.fun = self.fun.specialise(self.n, parameters, self._advanced)
         if parameters is None:
             parameters = self.fun.bound_parameters
         P = self.fun.P
@@ -211,7 +213,12 @@ class Ensemble:
 
     t = property(lambda s: s._scalar_or_array(s._get(_lib.F_T, None)))
     y = property(lambda s: s._scalar_or_array(s._get(_lib.F_Y, s.n)))
-    auxiliary = property(lambda s: s._scalar_or_array(s._get(_lib.F_AUX, s.Q)))
+    @property
+    def auxiliary(self):
+        a = self._get(_lib.F_AUX, self.Q)
+        if getattr(self.fun, 'aux_scalar', False):  # the Python RHS returned a scalar auxiliary (README.md:84)
+            a = a[:, 0]
+        return self._scalar_or_array(a)
     step_size = property(lambda s: s._scalar_or_array(s._get(_lib.F_STEP_SIZE, None)))
     direction = property(lambda s: s._scalar_or_array(s._get(_lib.F_DIRECTION, None)))
     parameters = property(lambda s: s._scalar_or_array(s._get(_lib.F_PARAMS, s.P)))

@@ -120,6 +120,9 @@ struct NiA {
   }
 };
 
+// sign(x) for translated Python right-hand sides (np.sign)
+NI_DEV double ni_sign(double x) { return (double)((x > 0.0) - (x < 0.0)); }
+
 // ---------------------------------------------------------------- utilities
 template <int I>
 struct NiInt {

@@ -260,3 +260,77 @@ def test_user_stencil_snippet_matches_builtin_heat():
     var = ni.CudaStencilRHS('const double k = p[0] * (1.0 + (double)j / n); return k * (ym - 2.0 * yc + yp);', P=1)
     c = ni.RK23(var, 0.0, w.y0, 0.5, rtol=1e-6, atol=1e-8, parameters=w.params)
     assert c.run() == 0 and np.all(np.isfinite(c.y)) and np.all(c.t == 0.5)
+
+
+def _maybe_njit(*sig):
+    """The reference's users hand numba-compiled functions to the solvers; decorate like the README does when
+    numba is importable (the facade only reads `.py_func`'s source, it never calls the function)."""
+    try:
+        import numba as nb
+        return nb.njit(*sig) if sig else nb.njit
+    except Exception:  # pragma: no cover
+        return lambda f: f
+
+
+def test_readme_example_verbatim_with_a_python_rhs():  # README.md:47-69, unchanged except the import
+    try:
+        import numba as nb
+        deco = nb.njit(nb.float64[:](nb.float64, nb.float64[:]))
+    except Exception:  # pragma: no cover
+        deco = lambda f: f  # noqa: E731
+
+    @deco
+    def f(t, y):
+        '''Differential equation for sine wave'''
+        return np.array((y[1], -y[0]))
+
+    y0 = np.array((0., 1.))
+    solver = ni.RK45(f, 0.0, y0, t_bound=1, atol=1e-8, rtol=1e-8)
+    t, y = [], []
+    while ni.step(solver):
+        t.append(solver.t)
+        y.append(solver.y)
+    meta, g = load_golden('c1_readme_sine_rk45')
+    assert t == g['rec_t'][0].tolist()                         # bit-identical to the reference's own run
+    assert np.array_equal(np.array(y), g['rec_y'][0])
+
+
+def test_readme_advanced_example_verbatim_with_a_python_rhs():  # README.md:74-111
+    @_maybe_njit()
+    def f(t, y, parameters):
+        '''Differential equation for sine wave'''
+        auxiliary = parameters[0] * y[1]
+        dy = np.array((auxiliary, -y[0])) + parameters[1]
+        return dy, auxiliary
+
+    t0 = 0.
+    y0 = np.array((0., 1.))
+    parameters = (2., np.array((-1., 1.)))
+    Solver = ni.Advanced(None, None, ni.RK45)                  # numba type signatures are not needed here
+    solver = Solver(f, t0, y0, parameters, t_bound=1, atol=1e-8, rtol=1e-8)
+    t, y, auxiliary = [], [], []
+    while ni.step(solver):
+        t.append(solver.t)
+        y.append(solver.y)
+        auxiliary.append(solver.auxiliary)
+    meta, g = load_golden('readme_advanced_rk45')
+    k = len(t)
+    assert k == g['n_accepted'][0] and isinstance(auxiliary[-1], float)
+    assert t == g['rec_t'][0, :k].tolist() and np.array_equal(np.array(y), g['rec_y'][0, :k])
+    assert auxiliary[-1] == g['aux'][0, 0]
+
+
+def test_python_rhs_ensemble_matches_builtin_lorenz():
+    def lorenz(t, y, p):
+        x, yy, z = y[0], y[1], y[2]
+        dy = np.array((p[0] * (yy - x), x * (p[1] - z) - yy, x * yy - p[2] * z))
+        return dy, np.array(((x * x + yy * yy) + z * z,))
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c3_lorenz(N=2000, t_bound=1.0)
+    a = ni.Advanced(None, None, ni.RK45)(lorenz, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    b = ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    a.run()
+    b.run()
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.auxiliary, b.auxiliary)
+    with pytest.raises(ni.TranslationError):
+        ni.RK45(lambda t, y: np.linalg.solve(np.eye(2), y), 0.0, np.ones(2), 1.0)

@@ -58,7 +58,9 @@ def test_advanced_factory_shapes():
 
 def test_rhs_validation():
     with pytest.raises(TypeError):
-        ni.RK45(lambda t, y: y, 0.0, np.ones(2), 1.0)
+        ni.RK45(42, 0.0, np.ones(2), 1.0)                       # not an RHS at all
+    with pytest.raises(ni.TranslationError):                    # Python RHS outside the translatable subset
+        ni.RK45(lambda t, y: np.linalg.inv(y), 0.0, np.ones(2), 1.0)
     with pytest.raises(ValueError):
         ni.RK45(ni.rhs.harmonic, 0.0, np.ones(3), 1.0)          # wrong dimension
     with pytest.raises(ValueError):
