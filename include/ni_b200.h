@@ -102,6 +102,9 @@ int ni_device_count(int *count);
 #define NI_MODE_ADVANCED 1 /* step_advanced semantics (h = h_abs*direction), parameters + auxiliary */
 #define NI_MODE_FAST 2     /* opt-in fast arithmetic: contracted multiply-adds, approximate reciprocal and
                               controller root (agrees with the reference to tolerance, not bit for bit) */
+#define NI_MODE_SCIPY 4    /* opt-in scipy.integrate.RK23/RK45 step semantics instead of the reference's: fresh FSAL
+                              stage on retries, no growth after a rejection, 10 ulp minimum step tested before each
+                              attempt, h = t_new - t, scipy's select_initial_step (SURVEY.md A.2 lists the differences) */
 int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module **out);
 /* `rhs_body` is the body of
  *   __device__ void rhs(double t, const double* y, const double* p, double* dy, double* aux)
@@ -153,6 +156,7 @@ int ni_ensemble_get(ni_ensemble *e, int field, void *host_out);
 int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in); /* NI_F_T_BOUND, NI_F_H_ABS */
 int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr);  /* zero-copy view (NCCL gather) */
 int ni_ensemble_set_max_attempts(ni_ensemble *e, int64_t per_launch);
+
 
 /* ---- recording of accepted steps into an HBM append log --------------------------------
  * (README.md:62-69 appends solver.t / solver.y after every accepted step.)  Records are

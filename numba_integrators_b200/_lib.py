@@ -14,7 +14,7 @@ LIB_PATH = PKG / 'libni_b200.so'
 NI_OK, NI_ERR_INVALID, NI_ERR_CUDA, NI_ERR_NVRTC, NI_ERR_UNSUPPORTED, NI_ERR_NOMEM, NI_ERR_REC_OVERFLOW = \
     0, -1, -2, -3, -4, -5, -6
 RK23, RK45 = 0, 1
-MODE_ADVANCED, MODE_FAST = 1, 2
+MODE_ADVANCED, MODE_FAST, MODE_SCIPY = 1, 2, 4
 (F_T, F_Y, F_AUX, F_H_ABS, F_STEP_SIZE, F_KLAST, F_STATUS, F_N_ACCEPTED, F_N_REJECTED, F_RUNNING, F_T_BOUND,
  F_DIRECTION, F_PARAMS, F_COND_HIT) = range(14)
 F_REC_TRAJ, F_REC_STEP, F_REC_T, F_REC_Y, F_REC_AUX = 20, 21, 22, 23, 24  # device_ptr only (record log)

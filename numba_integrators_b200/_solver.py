@@ -118,7 +118,8 @@ class Ensemble:
     """
 
     def __init__(self, fun, t0, y0, t_bound, max_step, rtol, atol, first_step, method, advanced=False,
-                 parameters=None, device=None, record=0, allow_reference_backward_bug=False, arithmetic='strict'):
+                 parameters=None, device=None, record=0, allow_reference_backward_bug=False, arithmetic='strict',
+                 semantics='reference'):
         self._h = None
         self._mod = None
         self._L = _lib.lib()
@@ -140,7 +141,10 @@ class Ensemble:
         self._first_step = float(first_step)
         t0a = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (self.N,)))
         tba = np.ascontiguousarray(np.broadcast_to(np.asarray(t_bound, dtype=np.float64), (self.N,)))
-        if not self._advanced and not allow_reference_backward_bug and np.any(tba < t0a):
+        if semantics not in ('reference', 'scipy'):
+            raise ValueError("semantics must be 'reference' (numba-integrators, quirks included) or 'scipy'")
+        self.semantics = semantics
+        if not self._advanced and semantics == 'reference' and not allow_reference_backward_bug and np.any(tba < t0a):
             raise ValueError('the basic RK23/RK45 ignore `direction` when forming the step (_basic.py:148) and '
                              'never reach a t_bound < t0; build the solver through ni.Advanced for backward runs')
         if isinstance(self.fun, PythonRHS):  # translate the Python source into a CUDA snippet (never executed)
@@ -169,7 +173,8 @@ class Ensemble:
                              "'fast' (contracted multiply-adds, approximate reciprocal / controller root)")
         self.arithmetic = arithmetic
         self._mod = self.fun._module(self.n, method, (_lib.MODE_ADVANCED if self._advanced else 0)
-                                     | (_lib.MODE_FAST if arithmetic == 'fast' else 0))
+                                     | (_lib.MODE_FAST if arithmetic == 'fast' else 0)
+                                     | (_lib.MODE_SCIPY if semantics == 'scipy' else 0))
         kind = C.c_int(0)
         check(self._L.ni_module_layout(self._mod, kind))
         self.kind = kind.value  # 0: component-major device buffers, 1: trajectory-major

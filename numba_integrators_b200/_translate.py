@@ -61,11 +61,7 @@ class _Translator:
             src = textwrap.dedent(inspect.getsource(self.pyfun))
         except (OSError, TypeError) as e:
             raise TranslationError(f'cannot read the source of {fun!r}: {e}') from e
-        tree = ast.parse(src)
-        fdefs = [nd for nd in ast.walk(tree) if isinstance(nd, (ast.FunctionDef, ast.Lambda))]
-        if not fdefs:
-            raise TranslationError('no function definition found')
-        self.fdef = fdefs[0]
+        self.fdef = self._find_function(src)
         args = [a.arg for a in self.fdef.args.args]
         if len(args) not in (2, 3):
             raise TranslationError(f'the right-hand side must take (t, y) or (t, y, parameters), got {args}')
@@ -90,6 +86,29 @@ class _Translator:
                     pass
         self.dy = self.aux = None
         self.aux_scalar = False
+
+    def _find_function(self, src):
+        """The FunctionDef / Lambda node of the right-hand side inside `src` (inspect.getsource gives the whole
+        statement for a lambda, possibly cut in the middle of a call that spans several lines)."""
+        want = self.pyfun.__code__.co_argcount
+        trees = []
+        try:
+            trees.append(ast.parse(src))
+        except SyntaxError:
+            pos = src.find('lambda')
+            while pos >= 0:  # grow-and-shrink: the longest prefix starting at this `lambda` that parses
+                for end in range(len(src), pos + 6, -1):
+                    try:
+                        trees.append(ast.parse(src[pos:end].strip().rstrip(','), mode='eval'))
+                        break
+                    except SyntaxError:
+                        continue
+                pos = src.find('lambda', pos + 6)
+        for tree in trees:
+            for nd in ast.walk(tree):
+                if isinstance(nd, (ast.FunctionDef, ast.Lambda)) and len(nd.args.args) == want:
+                    return nd
+        raise TranslationError(f'cannot find the definition of {self.pyfun.__name__} in its source')
 
     # ---- parameters: a flat float64 vector on the device; tuples of scalars / arrays are laid out in order
     def _param_struct(self, parameters):

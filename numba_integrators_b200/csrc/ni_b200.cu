@@ -58,7 +58,7 @@ NI_API int ni_device_count(int *count) {
 // ------------------------------------------------------------------ modules
 struct ni_module {
   int kind = NI_KIND_SMALL;
-  int n = 0, P = 0, Q = 0, method = NI_RK45, advanced = 0, fast = 0, S = 6;
+  int n = 0, P = 0, Q = 0, method = NI_RK45, advanced = 0, fast = 0, scipy = 0, S = 6;
   const void *k_init = nullptr;
   const void *k_run[2] = {nullptr, nullptr};  // [record]
   int block = NI_BLOCK;
@@ -86,12 +86,14 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module 
   *out = nullptr;
   if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
   if (n < 1) return fail(NI_ERR_INVALID, "n must be >= 1");
-  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
-  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0;
+  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST | NI_MODE_SCIPY)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
+  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0,
+            scipy = (mode & NI_MODE_SCIPY) ? 1 : 0;
   ni_module *m = new ni_module;
   m->method = method;
   m->advanced = advanced;
   m->fast = fast;
+  m->scipy = scipy;
   m->S = method == NI_RK45 ? 6 : 3;
   if (const NiKernelSet *ks = builtin_small(rhs_id, n)) {
     m->kind = NI_KIND_SMALL;
@@ -99,14 +101,14 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module 
     m->P = ks->P;
     m->Q = ks->Q;
     m->k_init = ks->init[method];
-    m->k_run[0] = ks->run[method][advanced][0][fast];
-    m->k_run[1] = ks->run[method][advanced][1][fast];
+    m->k_run[0] = ks->run[method][scipy ? 2 : advanced][0][fast];
+    m->k_run[1] = ks->run[method][scipy ? 2 : advanced][1][fast];
     *out = m;
     return NI_OK;
   }
-  if (fast && (rhs_id == NI_RHS_HEAT1D || rhs_id == NI_RHS_BURGERS1D)) {
+  if ((fast || scipy) && (rhs_id == NI_RHS_HEAT1D || rhs_id == NI_RHS_BURGERS1D)) {
     delete m;
-    return fail(NI_ERR_UNSUPPORTED, "NI_MODE_FAST is implemented for the thread-per-trajectory kernels only");
+    return fail(NI_ERR_UNSUPPORTED, "NI_MODE_FAST / NI_MODE_SCIPY are implemented for the thread-per-trajectory kernels only");
   }
   if (ni_large_builtin(rhs_id, n, method, advanced, &m->large, &m->P, &m->Q)) {
     m->kind = NI_KIND_LARGE;
@@ -230,8 +232,9 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   if (n > NI_MAX_SMALL_N)
     return fail(NI_ERR_UNSUPPORTED, "dense user RHS snippets support n <= %d (got %d); larger systems must be "
                 "3-point stencils (ni_module_compile_stencil)", NI_MAX_SMALL_N, n);
-  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
-  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0;
+  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST | NI_MODE_SCIPY)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
+  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0,
+            scipy = (mode & NI_MODE_SCIPY) ? 1 : 0;
   std::string src;
   src += "#include \"ni_core.cuh\"\n";
   src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
@@ -241,7 +244,7 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
   src += rhs_body;
   src += "\n  }\n};\n";
-  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false",
+  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = scipy ? "2" : advanced ? "1" : "0",
                     F = fast ? "true" : "false";
   src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
          "ni_small_init_body<NiUserRhs, " + M + ">(a); }\n";
@@ -258,6 +261,7 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
     return rc;
   }
   m->fast = fast;
+  m->scipy = scipy;
   m->kind = NI_KIND_SMALL;
   m->n = n;
   m->P = P;
@@ -330,7 +334,7 @@ NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *metho
   if (P) *P = m->P;
   if (Q) *Q = m->Q;
   if (method) *method = m->method;
-  if (advanced) *advanced = m->advanced | (m->fast ? NI_MODE_FAST : 0);
+  if (advanced) *advanced = m->advanced | (m->fast ? NI_MODE_FAST : 0) | (m->scipy ? NI_MODE_SCIPY : 0);
   if (n_stages) *n_stages = m->S;
   return NI_OK;
 }
@@ -454,6 +458,7 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
   NI_TRY(dalloc(e, &a.n_rej, sN))
   NI_TRY(dalloc(e, &a.running, sN))
   NI_TRY(dalloc(e, &a.cond_hit, sN))
+  NI_TRY(dalloc(e, &a.step_rejected, sN))
   NI_TRY(dalloc(e, &a.queue, 8))
   NI_TRY(dalloc(e, &a.rec_cursor, 1))
   NI_TRY(dalloc(e, &e->y0_rows, sN * n))
@@ -483,6 +488,7 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
   cudaMemsetAsync(a.rec_cursor, 0, sizeof(unsigned long long), e->stream);
   cudaMemsetAsync(a.cond_hit, 0, sN, e->stream);
   a.rec_cap = 0;
+  a.compat = m->scipy;
   a.max_step = __builtin_inf();
   a.first_step = 0.0;
   a.y0_rows = e->y0_rows;
@@ -574,6 +580,7 @@ NI_API int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *a
   e->a.max_step = max_step;
   e->a.first_step = first_step;
   CU(cudaMemsetAsync(e->a.cond_hit, 0, (size_t)e->N, e->stream));
+  CU(cudaMemsetAsync(e->a.step_rejected, 0, (size_t)e->N, e->stream));
   CU(cudaMemsetAsync(e->a.rec_cursor, 0, sizeof(unsigned long long), e->stream));
   CU(cudaEventRecord(e->ev[0], e->stream));
   int grid;

@@ -76,6 +76,8 @@ struct NiArgs {
   int n;                        // large kernels: state dimension (run-time)
   const double *rtol_d, *atol_d;  // large kernels: tolerance vectors in HBM (n entries)
   int tol_uniform;              // large kernels: every component has rtol[0] / atol[0]
+  int compat;                   // 0: the reference's step semantics; 1: scipy.integrate semantics
+  unsigned char *step_rejected; // compat == 1: "a rejection happened in the current step" (scipy's step_rejected)
   unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted
   long long max_attempts;       // per trajectory per launch (bounds kernel time)
   long long max_accepts;        // 1 = lock-step ni.step(), huge = fast-forward
@@ -382,7 +384,35 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
     Rhs::template eval<false>(t0, y, p, f0, aux);
     const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
     double h_abs;
-    if (a.first_step == 0.0) {
+    if (a.first_step != 0.0) {
+      h_abs = fabs(a.first_step);
+    } else if (a.compat != 0) {
+      // scipy.integrate._ivp.common.select_initial_step: no fastmath contractions, h0 capped by the interval,
+      // h1 = (0.01 / max(d1, d2)) ** (1 / (order + 1)), result capped by the interval and max_step
+      const double interval = fabs(__dadd_rn(tb, -t0));
+      double scale[n], tmp[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) scale[i] = __dadd_rn(a.atol[i], __dmul_rn(fabs(y[i]), a.rtol[i]));
+#pragma unroll
+      for (int i = 0; i < n; ++i) tmp[i] = y[i] / scale[i];
+      const double d0 = ni_rms<n>(tmp);
+#pragma unroll
+      for (int i = 0; i < n; ++i) tmp[i] = f0[i] / scale[i];
+      const double d1 = ni_rms<n>(tmp);
+      double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : __dmul_rn(0.01, d0) / d1;
+      h0 = fmin(h0, interval);
+      const double hd = __dmul_rn(h0, dir);
+      double y1[n], f1[n], auxd[Q > 0 ? Q : 1];
+#pragma unroll
+      for (int i = 0; i < n; ++i) y1[i] = __dadd_rn(y[i], __dmul_rn(hd, f0[i]));
+      Rhs::template eval<false>(__dadd_rn(t0, hd), y1, p, f1, auxd);
+#pragma unroll
+      for (int i = 0; i < n; ++i) tmp[i] = __dadd_rn(f1[i], -f0[i]) / scale[i];
+      const double d2 = ni_rms<n>(tmp) / h0;
+      const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, __dmul_rn(h0, 1e-3))
+                                                     : pow(0.01 / fmax(d1, d2), 1.0 / (NiTab<METHOD>::ORDER + 1));
+      h_abs = interval == 0.0 ? 0.0 : fmin(fmin(__dmul_rn(100.0, h0), h1), fmin(interval, a.max_step));
+    } else {
       double scale[n], tmp[n];
 #pragma unroll
       for (int i = 0; i < n; ++i) scale[i] = fma(fabs(y[i]), a.rtol[i], a.atol[i]);
@@ -407,8 +437,6 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
       else
         h1 = ni_pow_init<NiTab<METHOD>::ORDER + 1>(__dmul_rn(fmax(d1, d2), 100.0));
       h_abs = fmin(__dmul_rn(100.0, h0), h1);
-    } else {
-      h_abs = fabs(a.first_step);
     }
     a.t[idx] = t0;
     a.t_bound[idx] = tb;
@@ -437,8 +465,11 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
 // diverges inside the stage loop).  A lane retires its trajectory when it finished, failed,
 // used up max_accepts / max_attempts, hit the ff2cond predicate or found the record log full;
 // it then pulls the next trajectory index from the queue.
-template <class Rhs, int METHOD, bool ADV, bool REC, bool FAST = false>
+// SEM: 0 = the reference's basic solvers (_step), 1 = Advanced (step_advanced: h = h_abs*direction),
+// 2 = scipy.integrate step semantics (NI_MODE_SCIPY)
+template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
+  constexpr bool ADV = SEM >= 1, SP = SEM == 2;
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
   using Tab = NiTab<METHOD>;
   constexpr int S = Tab::S;
@@ -447,7 +478,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   const unsigned lane = threadIdx.x & 31u;
 
   long long idx = 0;
-  bool active = false, exhausted = false, fresh = true, last_accept = false, parked = false;
+  bool active = false, exhausted = false, fresh = true, last_accept = false, parked = false, srej = false;
   double t = 0, h_abs = 0, tb = 0, dir = 1, eps = 0, min_step = 0, step_h = 0;
   double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
   int nacc = 0, nrej = 0, status = NI_ST_RUNNING;
@@ -469,6 +500,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     a.n_acc[idx] = nacc;
     a.n_rej[idx] = nrej;
     a.running[idx] = last_accept ? 1 : 0;
+    if (SP) a.step_rejected[idx] = srej ? 1 : 0;
     if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
     if (last_accept) atomicAdd(a.queue + 3, 1ull);
     active = false;
@@ -510,6 +542,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           fresh = true;
           last_accept = false;
           parked = false;
+          srej = SP ? a.step_rejected[idx] != 0 : false;
           active = true;
         } else if (status >= 0) {
           a.running[idx] = 0;  // step() on a finished / failed solver returns False
@@ -527,23 +560,29 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         retire();
       } else {
         eps = ni_ulp_eps(t, dir);
-        min_step = __dmul_rn(8.0, eps);
-        if (h_abs < min_step) h_abs = min_step;
+        min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);  // scipy: 10 ulp
+        if (SP && h_abs > a.max_step)
+          h_abs = a.max_step;
+        else if (h_abs < min_step)
+          h_abs = min_step;
         fresh = false;
       }
     }
 
     // ---- one attempt (_basic.py:145-169)
-    bool ok = false;
+    bool ok = false, sp_fail = false;
     double tn = 0, h = 0, h_pre = 0, en = 0;
     double kn[n], yn[n], auxn[Q > 0 ? Q : 1];
     if (active) {
       h_pre = h_abs;
-      if (h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
-      h = ADV ? __dmul_rn(h_abs, dir) : h_abs;
+      sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt and commits nothing
+      if (!SP && h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+      h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
       tn = __dadd_rn(t, h);
-      if (__dmul_rn(dir, __dadd_rn(tn, -tb)) >= 0.0) {
-        tn = tb;
+      const double cross = __dmul_rn(dir, __dadd_rn(tn, -tb));
+      const bool clip = SP ? cross > 0.0 : cross >= 0.0;
+      if (clip) tn = tb;
+      if (clip || SP) {  // scipy recomputes h = t_new - t on every attempt
         h = __dadd_rn(tn, -t);
         h_abs = fabs(h);
       }
@@ -584,7 +623,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         }
         en = ni_rms<n>(ev);
       }
-      ok = en < 1.0;
+      ok = en < 1.0 && !sp_fail;
       --att_left;
     }
 
@@ -622,14 +661,16 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     // ---- controller + commit (_basic.py:171-180), branch-free for the accept / reject split so that a
     // warp with both kinds of lanes runs the controller once
     if (active) {
-      const bool nan = !ok && !(en >= 1.0);
-      const bool park = REC && ok && slot >= a.rec_cap;  // log full: undo this attempt (state before an
-                                                         // attempt is exactly t, y, h_abs, K[-1])
+      const bool nan = en != en;
+      // park: log full -> undo this attempt (the state before an attempt is exactly t, y, h_abs, K[-1]);
+      // scipy's too-small-step exit also commits nothing of the attempt (ok is already false then)
+      const bool park = (REC && ok && slot >= a.rec_cap) || sp_fail;
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
       const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
-      const double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
-      const bool fail = !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
+      const bool fail = !SP && !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
       const bool take = (ok && !park) || fail;
       h_abs = park ? h_pre : (nan ? h_abs : h_new);
       t = take ? tn : t;
@@ -637,7 +678,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         y[i] = take ? yn[i] : y[i];
-        kl[i] = park ? kl[i] : kn[i];
+        kl[i] = (park || (SP && !ok)) ? kl[i] : kn[i];  // scipy keeps f(t, y) of the accepted point on a rejection
       }
 #pragma unroll
       for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
@@ -648,6 +689,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       att_left += park ? 1 : 0;
       fresh = accepted;
       last_accept = accepted;
+      if (!park) srej = !ok;
       if (REC && accepted) {
         const long long c = a.rec_cap;
         a.rec_traj[slot] = (unsigned int)idx;
@@ -659,9 +701,13 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         for (int i = 0; i < Q; ++i) a.rec_aux[i * c + slot] = aux[i];
       }
       // ---- rare exits
-      bool done = park || fail || nan || att_left <= 0 || (accepted && acc_left <= 0);
-      if (park) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
-      if (fail) status = NI_ST_FAILED;
+      // (kept as separate statements: the single || expression was miscompiled by nvcc 12.9 for the SEM = 2
+      // instantiation -- `accepted && acc_left <= 0` evaluated to false with accepted = 1, acc_left = 0)
+      bool done = park || fail || nan;
+      if (att_left <= 0) done = true;
+      if (accepted && acc_left <= 0) done = true;
+      if (park && !sp_fail) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+      if (fail || sp_fail) status = NI_ST_FAILED;
       if (nan) status = NI_ST_NONFINITE;
       if (accepted && a.cond_kind != 0 && ni_cond_test<n, Q>(a, y, aux)) {
         a.cond_hit[idx] = 1;
@@ -688,7 +734,7 @@ template <class Rhs, int METHOD>
 __global__ void __launch_bounds__(NI_BLOCK) ni_k_init(const NiArgs a) {
   ni_small_init_body<Rhs, METHOD>(a);
 }
-template <class Rhs, int METHOD, bool ADV, bool REC, bool FAST>
+template <class Rhs, int METHOD, int SEM, bool REC, bool FAST>
 __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(Rhs::N)) ni_k_run(const NiArgs a) {
-  ni_small_run_body<Rhs, METHOD, ADV, REC, FAST>(a);
+  ni_small_run_body<Rhs, METHOD, SEM, REC, FAST>(a);
 }

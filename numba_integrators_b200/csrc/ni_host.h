@@ -10,7 +10,7 @@ struct NiKernelSet {
   int kind;
   int n, P, Q;                  // n < 0: any dimension (large kernels take n at run time)
   const void *init[2];          // [method]
-  const void *run[2][2][2][2];  // [method][advanced][record][fast arithmetic]
+  const void *run[2][3][2][2];  // [method][semantics: basic, advanced, scipy][record][fast arithmetic]
 };
 
 #define NI_VISIBLE_INTERNAL __attribute__((visibility("hidden")))
@@ -25,10 +25,12 @@ struct NiKernelSet {
         RHS::P,                                                                               \
         RHS::Q,                                                                               \
         {(const void *)&ni_k_init<RHS, NI_RK23>, (const void *)&ni_k_init<RHS, NI_RK45>},     \
-        {{{NI_KR(RHS, NI_RK23, false, false), NI_KR(RHS, NI_RK23, false, true)},              \
-          {NI_KR(RHS, NI_RK23, true, false), NI_KR(RHS, NI_RK23, true, true)}},               \
-         {{NI_KR(RHS, NI_RK45, false, false), NI_KR(RHS, NI_RK45, false, true)},              \
-          {NI_KR(RHS, NI_RK45, true, false), NI_KR(RHS, NI_RK45, true, true)}}}};             \
+        {{{NI_KR(RHS, NI_RK23, 0, false), NI_KR(RHS, NI_RK23, 0, true)},                      \
+          {NI_KR(RHS, NI_RK23, 1, false), NI_KR(RHS, NI_RK23, 1, true)},                      \
+          {NI_KR(RHS, NI_RK23, 2, false), NI_KR(RHS, NI_RK23, 2, true)}},                     \
+         {{NI_KR(RHS, NI_RK45, 0, false), NI_KR(RHS, NI_RK45, 0, true)},                      \
+          {NI_KR(RHS, NI_RK45, 1, false), NI_KR(RHS, NI_RK45, 1, true)},                      \
+          {NI_KR(RHS, NI_RK45, 2, false), NI_KR(RHS, NI_RK45, 2, true)}}}};                   \
     return &ks;                                                                               \
   }
 
