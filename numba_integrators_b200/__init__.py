@@ -10,6 +10,7 @@ sm_100a; there is no CPU fallback.
 __version__ = '0.1.0'
 
 from . import _rhs as rhs
+from . import sr
 from ._lib import NiError
 from ._rhs import BuiltinRHS, CudaRHS, CudaStencilRHS, PythonRHS
 from ._translate import TranslationError, translate
@@ -18,5 +19,5 @@ from ._solver import (ALL, MAX_FACTOR, MIN_FACTOR, RK, RK23, RK45, SAFETY, Advan
                       y_below)
 
 __all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaRHS', 'CudaStencilRHS', 'PythonRHS', 'TranslationError', 'translate', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
-           'Records', 'Solver', 'Solvers', 'StepMask', 'aux_above', 'aux_below', 'convert', 'ff2cond', 'ff2t', 'rhs',
+           'Records', 'Solver', 'Solvers', 'StepMask', 'aux_above', 'aux_below', 'convert', 'ff2cond', 'ff2t', 'rhs', 'sr',
            'step', 'y_above', 'y_below', 'SAFETY', 'MIN_FACTOR', 'MAX_FACTOR']

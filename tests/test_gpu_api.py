@@ -334,3 +334,15 @@ def test_python_rhs_ensemble_matches_builtin_lorenz():
     assert np.array_equal(a.y, b.y) and np.array_equal(a.auxiliary, b.auxiliary)
     with pytest.raises(ni.TranslationError):
         ni.RK45(lambda t, y: np.linalg.solve(np.eye(2), y), 0.0, np.ones(2), 1.0)
+
+
+def test_structref_flavour():  # ni.sr (_structref.py): x / x_bound field names, applies direction
+    def f(t, y):
+        return np.array((y[1], -y[0]))
+    state = ni.sr.RK45(f, 1.0, np.array((0.3, -0.7)), 0.0, rtol=1e-8, atol=1e-8)   # backward
+    meta, g = load_golden('backward_harmonic_rk45')
+    k = 0
+    while ni.sr.step(state):
+        assert state.x == g['rec_t'][0, k] and np.array_equal(state.y, g['rec_y'][0, k])
+        k += 1
+    assert k == g['n_accepted'][0] == 10 and state.x == state.x_bound == 0.0
