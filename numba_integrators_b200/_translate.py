@@ -65,7 +65,9 @@ class _Translator:
         args = [a.arg for a in self.fdef.args.args]
         if len(args) not in (2, 3):
             raise TranslationError(f'the right-hand side must take (t, y) or (t, y, parameters), got {args}')
-        self.n, self.advanced = n, advanced
+        # `f(t, y, parameters)` returns (dy, auxiliary) (_advanced.py:22-26); `f(t, y)` returns dy, whichever step
+        # semantics the solver uses (ni.sr applies the Advanced semantics to a basic right-hand side)
+        self.n, self.advanced = n, len(args) == 3
         self.tname, self.yname = args[0], args[1]
         self.pname = args[2] if len(args) == 3 else None
         self.env = {}          # python name -> C scalar expr | Vec | int constant | _Params
