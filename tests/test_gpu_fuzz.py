@@ -1,0 +1,97 @@
+"""Randomised differential test: GPU (through the facade / C ABI) against the CPU oracle over random
+configurations -- method, right-hand side, tolerances (scalar and per-component), horizon, direction, max_step,
+first_step, per-trajectory t0 / t_bound, ensemble size (ragged), lock-step vs fast-forward vs ff2t legs."""
+import numpy as np
+import pytest
+
+import numba_integrators_b200 as ni
+
+pytestmark = pytest.mark.gpu
+
+RHS = {  # name -> (n, P, sampler of y0, sampler of params, typical horizon)
+    'harmonic': (2, 0, lambda r, N: r.uniform(-1, 1, (N, 2)), None, 6.0),
+    'lorenz63': (3, 3, lambda r, N: np.column_stack([r.uniform(-10, 10, (N, 2)), r.uniform(15, 35, N)]),
+                 lambda r, N: np.column_stack([r.uniform(9, 11, N), r.uniform(26, 30, N), r.uniform(2.5, 2.8, N)]), 0.8),
+    'vanderpol': (2, 1, lambda r, N: r.uniform(-2, 2, (N, 2)), lambda r, N: r.uniform(0.1, 4.0, (N, 1)), 4.0),
+    'exponential': (1, 0, lambda r, N: r.uniform(0.5, 2, (N, 1)), None, 3.0),
+    'riccati': (1, 0, lambda r, N: r.uniform(0.5, 1.5, (N, 1)), None, 5.0),
+}
+
+
+def make_case(seed):
+    r = np.random.default_rng(seed)
+    name = list(RHS)[seed % len(RHS)]
+    n, P, ys, ps, T = RHS[name]
+    N = int(r.integers(1, 200))
+    cfg = dict(name=name, method=['RK45', 'RK23'][int(r.integers(2))], N=N, y0=ys(r, N),
+               params=None if ps is None else ps(r, N))
+    tol = 10.0 ** r.uniform(-10, -4)
+    cfg['rtol'] = tol * 10.0 ** r.uniform(-0.5, 0.5, n) if r.random() < 0.3 else tol
+    cfg['atol'] = tol * 10.0 ** r.uniform(-2, 0, n) if r.random() < 0.3 else tol * 0.1
+    t0 = 1.0 if name == 'riccati' else 0.0
+    span = T * r.uniform(0.3, 1.0)
+    cfg['advanced'] = bool(r.random() < 0.5) or P > 0
+    backward = cfg['advanced'] and name != 'riccati' and r.random() < 0.25
+    if r.random() < 0.3:                                         # per-trajectory times
+        cfg['t0'] = t0 + r.uniform(0, 0.2, N)
+        cfg['t_bound'] = cfg['t0'] + (-1 if backward else 1) * span * r.uniform(0.5, 1.0, N)
+    else:
+        cfg['t0'], cfg['t_bound'] = t0, t0 + (-span if backward else span)
+    cfg['max_step'] = span / r.integers(5, 50) if r.random() < 0.3 else np.inf
+    cfg['first_step'] = span * 10.0 ** r.uniform(-4, -2) if r.random() < 0.3 else 0.0
+    cfg['driver'] = ['run', 'step', 'ff2t'][int(r.integers(3))]
+    return cfg
+
+
+def build(cfg):
+    f = ni.BuiltinRHS(cfg['name'])
+    kw = dict(max_step=cfg['max_step'], rtol=cfg['rtol'], atol=cfg['atol'], first_step=cfg['first_step'])
+    if cfg['advanced']:
+        ctor = ni.Advanced(f.P, f.Q, ni.RK45 if cfg['method'] == 'RK45' else ni.RK23)
+        return ctor(f, cfg['t0'], cfg['y0'], cfg['params'], cfg['t_bound'], **kw)
+    ctor = ni.RK45 if cfg['method'] == 'RK45' else ni.RK23
+    return ctor(f, cfg['t0'], cfg['y0'], cfg['t_bound'], **kw)
+
+
+@pytest.mark.parametrize('seed', range(60))
+def test_random_configuration_matches_oracle(seed, oracle):
+    cfg = make_case(seed)
+    s = build(cfg)
+    if cfg['driver'] == 'run':
+        assert s.run() == 0
+    elif cfg['driver'] == 'step':
+        k = 0
+        while ni.step(s):
+            k += 1
+            assert k < 100000
+    else:                                                        # three ff2t legs; the legs change the step sequence
+        fwd = np.all(np.atleast_1d(cfg['t_bound']) > np.atleast_1d(cfg['t0']))
+        if not fwd:
+            s.run()                                              # ff2t is forward-only in the reference (_API.py:31)
+        else:
+            lo, hi = float(np.max(cfg['t0'])), float(np.min(cfg['t_bound']))
+            for frac in (0.3, 0.7):
+                ni.ff2t(s, lo + frac * (hi - lo))
+            s.run()
+    m = oracle.RK45 if cfg['method'] == 'RK45' else oracle.RK23
+    N = cfg['N']
+    t0 = np.broadcast_to(np.asarray(cfg['t0'], float), (N,))
+    tb = np.broadcast_to(np.asarray(cfg['t_bound'], float), (N,))
+    y, t = np.atleast_2d(s.y), np.atleast_1d(s.t)
+    acc, rej = np.atleast_1d(s.n_accepted), np.atleast_1d(s.n_rejected)
+    bad = 0
+    for i in range(N):
+        o = oracle.OracleSolver(cfg['name'], m, t0[i], cfg['y0'][i], tb[i],
+                                params=None if cfg['params'] is None else cfg['params'][i], max_step=cfg['max_step'],
+                                rtol=cfg['rtol'], atol=cfg['atol'], first_step=cfg['first_step'],
+                                advanced=cfg['advanced'])
+        if cfg['driver'] == 'ff2t' and np.all(tb > t0):
+            lo, hi = float(np.max(t0)), float(np.min(tb))
+            for frac in (0.3, 0.7):
+                oracle.ff2t(o, lo + frac * (hi - lo))
+        while o.step():
+            pass
+        rel = np.max(np.abs(y[i] - o.y)) / max(np.max(np.abs(o.y)), 1e-300)
+        if not (t[i] == o.t and acc[i] == o.n_accepted and rej[i] == o.n_rejected and rel <= 1e-11):
+            bad += 1
+    assert bad <= max(1, N // 100), (cfg['name'], cfg['method'], cfg['driver'], bad, N)
