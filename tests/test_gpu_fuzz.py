@@ -31,7 +31,9 @@ def make_case(seed):
     t0 = 1.0 if name == 'riccati' else 0.0
     span = T * r.uniform(0.3, 1.0)
     cfg['advanced'] = bool(r.random() < 0.5) or P > 0
-    backward = cfg['advanced'] and name != 'riccati' and r.random() < 0.25
+    # backward Lorenz is violently expanding (~e^{13.7 t}): 1e4+ steps whose 1-ulp `pow` differences (glibc misrounds
+    # ~5e-4 of calls) are amplified far above any tolerance -- a conditioning property, not a parity one
+    backward = cfg['advanced'] and name not in ('riccati', 'lorenz63') and r.random() < 0.25
     if r.random() < 0.3:                                         # per-trajectory times
         cfg['t0'] = t0 + r.uniform(0, 0.2, N)
         cfg['t_bound'] = cfg['t0'] + (-1 if backward else 1) * span * r.uniform(0.5, 1.0, N)
