@@ -374,7 +374,8 @@ def main():
             if tr:
                 roofline['traffic'] = tr['bytes_per_trajectory'] * N
                 roofline['traffic_source'] = tr['capture']
-                roofline['algorithmic_bytes'] = N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13)
+                roofline['algorithmic_bytes'] = (N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13)
+                                                 + (w.record_bytes_per_step * acc_rank if record else 0))
         except (OSError, ValueError):
             pass
         if record:  # C2: recording-heavy -- report the HBM side of the ridge as well

@@ -467,6 +467,12 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
 // it then pulls the next trajectory index from the queue.
 // SEM: 0 = the reference's basic solvers (_step), 1 = Advanced (step_advanced: h = h_abs*direction),
 // 2 = scipy.integrate step semantics (NI_MODE_SCIPY)
+//
+// Loop structure: the hot part (one attempt + controller + commit for all 32 lanes) is branch-free and is
+// entered every iteration; lanes whose trajectory is done raise `need` and the warp takes the SERVICE branch
+// (store the retired state, pop the next trajectory from the queue, reload) only when some lane needs it --
+// about once per 18 iterations on C3.  Lanes without work keep executing the arithmetic on their stale
+// registers with every commit masked off.
 template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
   constexpr bool ADV = SEM >= 1, SP = SEM == 2;
@@ -476,56 +482,76 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   constexpr unsigned FULL = 0xffffffffu;
   const long long N = a.N;
   const unsigned lane = threadIdx.x & 31u;
+  const int max_att = a.max_attempts > 0x7fffffffLL ? 0x7fffffff : (int)a.max_attempts;
+  const int max_acc = a.max_accepts > 0x7fffffffLL ? 0x7fffffff : (int)a.max_accepts;
 
   long long idx = 0;
-  bool active = false, exhausted = false, fresh = true, last_accept = false, parked = false, srej = false;
-  double t = 0, h_abs = 0, tb = 0, dir = 1, eps = 0, min_step = 0, step_h = 0;
+  bool active = false, exhausted = false, need = true, fresh = true, last_accept = false, parked = false, srej = false;
+  double t = 0, h_abs = 0, tb = 0, dir = 1, step_h = 0;
   double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
+#pragma unroll
+  for (int i = 0; i < n; ++i) y[i] = kl[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < (P > 0 ? P : 1); ++i) p[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < (Q > 0 ? Q : 1); ++i) aux[i] = 0.0;
   int nacc = 0, nrej = 0, status = NI_ST_RUNNING;
-  long long att_left = 0, acc_left = 0;
+  int att_left = 0, acc_left = 0;
   long long rc_next = 0, rc_end = 0;  // REC: this warp's reserved slot range [rc_next, rc_end)
 
-  auto retire = [&]() {
-    a.t[idx] = t;
-    a.h_abs[idx] = h_abs;
-    a.step_size[idx] = step_h;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      a.y[i * N + idx] = y[i];
-      a.klast[i * N + idx] = kl[i];
-    }
-#pragma unroll
-    for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
-    a.status[idx] = status;
-    a.n_acc[idx] = nacc;
-    a.n_rej[idx] = nrej;
-    a.running[idx] = last_accept ? 1 : 0;
-    if (SP) a.step_rejected[idx] = srej ? 1 : 0;
-    if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
-    if (last_accept) atomicAdd(a.queue + 3, 1ull);
-    active = false;
-  };
-
   for (;;) {
-    // ---- refill: pull the next trajectory (warp-aggregated queue pop)
-    if (!active && !exhausted) {
-      const unsigned need = __activemask();
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(need, base, leader);
-      idx = (long long)(base + __popc(need & ((1u << lane) - 1u)));
-      if (idx >= N || (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW))) {
-        exhausted = true;
-      } else {
-        status = a.status[idx];
-        if (a.cond_kind != 0 && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
-        if (status == NI_ST_RUNNING) {
+    // ================================================================ SERVICE (rare)
+    if (__any_sync(FULL, need)) {
+      if (need) {
+        if (active) {  // retire: write the trajectory back
+          a.t[idx] = t;
+          a.h_abs[idx] = h_abs;
+          a.step_size[idx] = step_h;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            a.y[i * N + idx] = y[i];
+            a.klast[i * N + idx] = kl[i];
+          }
+#pragma unroll
+          for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
+          a.status[idx] = status;
+          a.n_acc[idx] = nacc;
+          a.n_rej[idx] = nrej;
+          a.running[idx] = last_accept ? 1 : 0;
+          if (SP) a.step_rejected[idx] = srej ? 1 : 0;
+          if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
+          if (last_accept) atomicAdd(a.queue + 3, 1ull);
+          active = false;
+        }
+        // refill: pop trajectories (warp-aggregated) until one is runnable or the queue is empty
+        while (!active && !exhausted) {
+          const unsigned grp = __activemask();
+          const int leader = __ffs(grp) - 1;
+          unsigned long long base = 0;
+          if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(grp));
+          base = __shfl_sync(grp, base, leader);
+          idx = (long long)(base + __popc(grp & ((1u << lane) - 1u)));
+          if (idx >= N || (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW))) {
+            exhausted = true;
+            break;
+          }
+          status = a.status[idx];
+          if (a.cond_kind != 0 && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
+          if (status != NI_ST_RUNNING) {
+            if (status >= 0) a.running[idx] = 0;  // step() on a finished / failed solver returns False
+            continue;
+          }
           t = a.t[idx];
           h_abs = a.h_abs[idx];
-          step_h = a.step_size[idx];
           tb = a.t_bound[idx];
           dir = a.direction[idx];
+          if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached (_basic.py:135-136)
+            a.step_size[idx] = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
+            a.status[idx] = NI_ST_FINISHED;
+            a.running[idx] = 0;
+            continue;
+          }
+          step_h = a.step_size[idx];
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             y[i] = a.y[i * N + idx];
@@ -537,55 +563,48 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           for (int i = 0; i < Q; ++i) aux[i] = a.aux[i * N + idx];
           nacc = a.n_acc[idx];
           nrej = a.n_rej[idx];
-          att_left = a.max_attempts;
-          acc_left = a.max_accepts;
+          att_left = max_att;
+          acc_left = max_acc;
           fresh = true;
           last_accept = false;
           parked = false;
           srej = SP ? a.step_rejected[idx] != 0 : false;
+          status = NI_ST_RUNNING;
           active = true;
-        } else if (status >= 0) {
-          a.running[idx] = 0;  // step() on a finished / failed solver returns False
         }
+        need = false;
       }
-    }
-    if (__all_sync(FULL, !active && exhausted)) break;
-
-    // ---- step entry (_basic.py:135-143)
-    if (active && fresh) {
-      if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached
-        step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
-        status = NI_ST_FINISHED;
-        last_accept = false;
-        retire();
-      } else {
-        eps = ni_ulp_eps(t, dir);
-        min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);  // scipy: 10 ulp
-        if (SP && h_abs > a.max_step)
-          h_abs = a.max_step;
-        else if (h_abs < min_step)
-          h_abs = min_step;
-        fresh = false;
-      }
+      if (__all_sync(FULL, !active)) break;
     }
 
+    // ================================================================ HOT: one attempt for every lane
+    const bool act = active;
+    // ---- step entry (_basic.py:139-143); recomputed per attempt: between retries t does not change and the
+    // clamp is a no-op (a retry only happens with h_abs >= min_step)
+    const double eps = ni_ulp_eps(t, dir);
+    const double min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);  // scipy: 10 ulp
+    if (SP) {
+      if (fresh) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
+    } else {
+      h_abs = h_abs < min_step ? min_step : h_abs;
+    }
     // ---- one attempt (_basic.py:145-169)
-    bool ok = false, sp_fail = false;
-    double tn = 0, h = 0, h_pre = 0, en = 0;
-    double kn[n], yn[n], auxn[Q > 0 ? Q : 1];
-    if (active) {
-      h_pre = h_abs;
-      sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt and commits nothing
-      if (!SP && h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
-      h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
-      tn = __dadd_rn(t, h);
+    const double h_pre = h_abs;
+    const bool sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt, commits nothing
+    if (!SP && h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+    double h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
+    double tn = __dadd_rn(t, h);
+    {
       const double cross = __dmul_rn(dir, __dadd_rn(tn, -tb));
       const bool clip = SP ? cross > 0.0 : cross >= 0.0;
-      if (clip) tn = tb;
+      tn = clip ? tb : tn;
       if (clip || SP) {  // scipy recomputes h = t_new - t on every attempt
         h = __dadd_rn(tn, -t);
         h_abs = fabs(h);
       }
+    }
+    double en, kn[n], yn[n], auxn[Q > 0 ? Q : 1];
+    {
       double K[S + 1][n];
 #pragma unroll
       for (int i = 0; i < n; ++i) K[0][i] = kl[i];  // K[0] = K[-1]: stale after a rejection (:151)
@@ -623,9 +642,8 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         }
         en = ni_rms<n>(ev);
       }
-      ok = en < 1.0 && !sp_fail;
-      --att_left;
     }
+    const bool ok = act && en < 1.0 && !sp_fail;
 
     // ---- record log: one slot per accepting lane.  A warp reserves `rec_chunk` slots with ONE atomicAdd
     // and hands them out locally (a single global cursor saturates the L2 atomic unit at ~0.8 G
@@ -658,38 +676,39 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       }
     }
 
-    // ---- controller + commit (_basic.py:171-180), branch-free for the accept / reject split so that a
-    // warp with both kinds of lanes runs the controller once
-    if (active) {
-      const bool nan = en != en;
+    // ---- controller + commit (_basic.py:171-180), branch-free: every update is a select on the lane's flags
+    {
+      const bool nan = act && en != en;
       // park: log full -> undo this attempt (the state before an attempt is exactly t, y, h_abs, K[-1]);
-      // scipy's too-small-step exit also commits nothing of the attempt (ok is already false then)
-      const bool park = (REC && ok && slot >= a.rec_cap) || sp_fail;
+      // scipy's too-small-step exit also commits nothing of the attempt
+      const bool park = (REC && ok && slot >= a.rec_cap) || (act && sp_fail);
+      const bool upd = act && !park;  // this attempt counts
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
       const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
       double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
       if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
-      const bool fail = !SP && !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
-      const bool take = (ok && !park) || fail;
-      h_abs = park ? h_pre : (nan ? h_abs : h_new);
+      const bool fail = upd && !SP && !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
+      const bool accepted = ok && !park;
+      const bool take = accepted || fail;
+      h_abs = upd ? (nan ? h_abs : h_new) : h_pre;
       t = take ? tn : t;
       step_h = (take || nan) ? h : step_h;
+      const bool newk = upd && !(SP && !ok);  // scipy keeps f(t, y) of the accepted point on a rejection
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         y[i] = take ? yn[i] : y[i];
-        kl[i] = (park || (SP && !ok)) ? kl[i] : kn[i];  // scipy keeps f(t, y) of the accepted point on a rejection
+        kl[i] = newk ? kn[i] : kl[i];
       }
 #pragma unroll
       for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
-      const bool accepted = ok && !park;
       nacc += accepted ? 1 : 0;
-      nrej += (ok || park) ? 0 : 1;
+      nrej += (upd && !ok) ? 1 : 0;
       acc_left -= accepted ? 1 : 0;
-      att_left += park ? 1 : 0;
-      fresh = accepted;
-      last_accept = accepted;
-      if (!park) srej = !ok;
+      att_left -= upd ? 1 : 0;
+      fresh = accepted ? true : (upd ? false : fresh);
+      last_accept = act ? accepted : last_accept;
+      srej = upd ? !ok : srej;
       if (REC && accepted) {
         const long long c = a.rec_cap;
         a.rec_traj[slot] = (unsigned int)idx;
@@ -700,16 +719,14 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) a.rec_aux[i * c + slot] = aux[i];
       }
-      // ---- rare exits
-      // (kept as separate statements: the single || expression was miscompiled by nvcc 12.9 for the SEM = 2
-      // instantiation -- `accepted && acc_left <= 0` evaluated to false with accepted = 1, acc_left = 0)
+      // ---- exits: raise `need` for the service branch
       bool done = park || fail || nan;
-      if (att_left <= 0) done = true;
+      if (upd && att_left <= 0) done = true;
       if (accepted && acc_left <= 0) done = true;
-      if (park && !sp_fail) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
-      if (fail || sp_fail) status = NI_ST_FAILED;
+      if (REC && park && !sp_fail) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+      if (fail || (act && sp_fail)) status = NI_ST_FAILED;
       if (nan) status = NI_ST_NONFINITE;
-      if (accepted && a.cond_kind != 0 && ni_cond_test<n, Q>(a, y, aux)) {
+      if (a.cond_kind != 0 && accepted && ni_cond_test<n, Q>(a, y, aux)) {
         a.cond_hit[idx] = 1;
         parked = true;
         done = true;
@@ -721,7 +738,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         last_accept = false;
         done = true;
       }
-      if (done) retire();
+      need = done;
     }
   }
   if (REC) {  // slots reserved but never written
