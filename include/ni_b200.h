@@ -152,6 +152,13 @@ int ni_ensemble_ff2t(ni_ensemble *e, double t_end, uint8_t *is_not_last);
 /* ni.ff2cond (_API.py:41-49) with a built-in predicate NI_COND_*; hit: uint8[N] or NULL. */
 int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double value, uint8_t *hit, int64_t *n_hit);
 
+/* ni.ff2cond with a user predicate (_API.py:41-49 takes any njit callable): `cond_body` is the body of
+ *   __device__ bool cond(double t, const double* y, const double* aux, const double* cp)
+ * fused (NVRTC) into this ensemble's run kernel and evaluated after every accepted step; cp = cond_params
+ * (0..8 doubles).  Thread-per-trajectory kernels only. */
+int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const double *cond_params, int n_params,
+                             uint8_t *hit, int64_t *n_hit);
+
 int ni_ensemble_get(ni_ensemble *e, int field, void *host_out);
 int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in); /* NI_F_T_BOUND, NI_F_H_ABS */
 int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr);  /* zero-copy view (NCCL gather) */

@@ -13,11 +13,12 @@ from . import _rhs as rhs
 from . import sr
 from ._lib import NiError
 from ._rhs import BuiltinRHS, CudaRHS, CudaStencilRHS, PythonRHS
-from ._translate import TranslationError, translate
-from ._solver import (ALL, MAX_FACTOR, MIN_FACTOR, RK, RK23, RK45, SAFETY, Advanced, Condition, Ensemble, Records,
+from ._translate import TranslationError, translate, translate_condition
+from ._solver import (ALL, MAX_FACTOR, MIN_FACTOR, RK, RK23, RK45, SAFETY, Advanced, Condition, CudaCondition, Ensemble,
+                      Records,
                       Solver, Solvers, StepMask, aux_above, aux_below, convert, ff2cond, ff2t, step, y_above,
                       y_below)
 
-__all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaRHS', 'CudaStencilRHS', 'PythonRHS', 'TranslationError', 'translate', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
+__all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaCondition', 'translate_condition', 'CudaRHS', 'CudaStencilRHS', 'PythonRHS', 'TranslationError', 'translate', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
            'Records', 'Solver', 'Solvers', 'StepMask', 'aux_above', 'aux_below', 'convert', 'ff2cond', 'ff2t', 'rhs', 'sr',
            'step', 'y_above', 'y_below', 'SAFETY', 'MIN_FACTOR', 'MAX_FACTOR']

@@ -50,6 +50,7 @@ SIGNATURES = {
     'ni_ensemble_sync': (C.c_int, [_vp]),
     'ni_ensemble_ff2t': (C.c_int, [_vp, C.c_double, _vp]),
     'ni_ensemble_ff2cond': (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, _vp, _i64p]),
+    'ni_ensemble_ff2cond_user': (C.c_int, [_vp, C.c_char_p, _dp, C.c_int, _vp, _i64p]),
     'ni_ensemble_get': (C.c_int, [_vp, C.c_int, _vp]),
     'ni_ensemble_set': (C.c_int, [_vp, C.c_int, _vp]),
     'ni_ensemble_device_ptr': (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),

@@ -291,6 +291,15 @@ class Ensemble:
         check(self._L.ni_ensemble_ff2t(self._h, float(t_end), flags.ctypes.data))
         return bool(flags[0]) if self._single else _mask(flags)
 
+    def ff2cond_user(self, body, cond_params):
+        """ff2cond with a CUDA predicate body `bool cond(double t, const double* y, const double* aux, const double* cp)`."""
+        cp = np.ascontiguousarray(np.atleast_1d(np.asarray(cond_params, dtype=np.float64)))
+        hit = np.zeros(self.N, dtype=np.uint8)
+        n_hit = C.c_int64(0)
+        check(self._L.ni_ensemble_ff2cond_user(self._h, str(body).encode(), cp.ctypes.data_as(_lib._dp), int(cp.size),
+                                               hit.ctypes.data, n_hit))
+        return bool(hit[0]) if self._single else _mask(hit)
+
     def ff2cond_device(self, kind, index, value):
         hit = np.zeros(self.N, dtype=np.uint8)
         n_hit = C.c_int64(0)
@@ -478,6 +487,15 @@ class Condition:
         self.kind, self.index = kind, index
 
 
+class CudaCondition:
+    """User predicate for ff2cond as CUDA C++: the body of
+    `bool cond(double t, const double* y, const double* aux, const double* cp)`; `cp` receives the
+    `parameters` argument of ff2cond (up to 8 doubles)."""
+
+    def __init__(self, body):
+        self.body = str(body)
+
+
 def y_above(index=0):
     return Condition(_lib.COND_Y_GT, index)
 
@@ -502,6 +520,19 @@ def ff2cond(solver, condition, parameters):
     lock-step `step()` exactly like _API.py:45-49."""
     if isinstance(condition, Condition):
         return solver.ff2cond_device(condition.kind, condition.index, parameters)
+    if isinstance(condition, CudaCondition):
+        return solver.ff2cond_user(condition.body, parameters)
+    if callable(condition) and solver.kind == 0:
+        # a Python predicate: translate its source and evaluate it inside the kernel; predicates outside the
+        # translatable subset fall back to the reference's own host loop over lock-step step() calls
+        from ._translate import TranslationError, translate_condition
+        try:
+            body, cp = translate_condition(condition, solver.n, solver.Q, getattr(solver.fun, 'aux_scalar', False),
+                                           parameters)
+        except TranslationError:
+            body = None
+        if body is not None:
+            return solver.ff2cond_user(body, cp)
     while solver.step():
         if condition(solver, parameters):
             return True

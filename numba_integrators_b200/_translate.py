@@ -484,3 +484,67 @@ def translate(fun, n, parameters=None, advanced=False):
     tr = _Translator(fun, int(n), parameters, bool(advanced))
     body = tr.run()
     return body, tr.P, len(tr.aux), tr.aux_scalar
+
+
+class _CondTranslator(_Translator):
+    """`condition(solver, parameters) -> bool` (_API.py:41-49): `solver.t`, `solver.y`, `solver.auxiliary` and the
+    predicate parameters are the only inputs a device predicate can see."""
+
+    def __init__(self, fun, n, Q, aux_scalar, parameters):
+        self.pyfun = getattr(fun, 'py_func', fun)
+        try:
+            src = textwrap.dedent(inspect.getsource(self.pyfun))
+        except (OSError, TypeError) as e:
+            raise TranslationError(f'cannot read the source of {fun!r}: {e}') from e
+        self.fdef = self._find_function(src)
+        args = [a.arg for a in self.fdef.args.args]
+        if len(args) != 2:
+            raise TranslationError(f'a predicate takes (solver, parameters), got {args}')
+        self.n, self.advanced = n, False
+        self.sname, self.pname = args
+        self.env, self.decl, self.lines = {}, set(), []
+        par = np.atleast_1d(np.asarray(parameters, dtype=np.float64)) if not isinstance(parameters, (tuple, list)) \
+            else np.concatenate([np.ravel(np.asarray(q, dtype=np.float64)) for q in parameters])
+        if par.size > 8:
+            raise TranslationError('a device predicate takes at most 8 parameters')
+        self.cond_params = par
+        if isinstance(parameters, (tuple, list)) or np.ndim(parameters) > 0:
+            self.env[self.pname] = Vec(f'cp[{i}]' for i in range(par.size))
+        else:
+            self.env[self.pname] = 'cp[0]'
+        aux = Vec(f'aux[{i}]' for i in range(Q))
+        self.attrs = {'t': 't', 'y': Vec(f'y[{i}]' for i in range(n)),
+                      'auxiliary': (aux[0] if aux_scalar and Q == 1 else aux)}
+        self.globals = dict(getattr(self.pyfun, '__globals__', {}))
+        self.result = None
+
+    def expr(self, node):
+        if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id == self.sname:
+            if node.attr in self.attrs:
+                return self.attrs[node.attr]
+            self.err(node, f'a device predicate can read solver.t, solver.y and solver.auxiliary, not solver.{node.attr}')
+        return super().expr(node)
+
+    def ret(self, node):
+        if self.result is not None:
+            self.err(node, 'more than one return statement')
+        v = node.value
+        self.result = self.cond(v) if isinstance(v, (ast.Compare, ast.BoolOp)) or \
+            (isinstance(v, ast.UnaryOp) and isinstance(v.op, ast.Not)) else f'({self.scalar(self.expr(v))} != 0.0)'
+
+    def run(self):
+        if isinstance(self.fdef, ast.Lambda):
+            self.ret(ast.Return(value=self.fdef.body))
+        else:
+            for st in self.fdef.body:
+                self.stmt(st)
+        if self.result is None:
+            raise TranslationError('the predicate has no return statement')
+        out = [f'double {cn} = 0.0;' for cn in sorted(self.decl)] + list(self.lines) + [f'return {self.result};']
+        return '\n'.join('    ' + ln for ln in out)
+
+
+def translate_condition(fun, n, Q=0, aux_scalar=False, parameters=0.0):
+    """Returns (cuda_body, parameter_vector) for a reference-style predicate `fun(solver, parameters)`."""
+    tr = _CondTranslator(fun, int(n), int(Q), bool(aux_scalar), parameters)
+    return tr.run(), tr.cond_params

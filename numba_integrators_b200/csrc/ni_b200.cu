@@ -26,6 +26,7 @@
 extern const char ni_core_source[];   // ni_core.cuh as a string (generated: ni_core_src.cpp)
 extern const char ni_math_source[];   // ni_math.cuh as a string
 extern const char ni_large_source[];  // ni_large.cuh as a string
+extern const char ni_rhs_builtin_source[];  // ni_rhs_builtin.cuh as a string
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -66,7 +67,22 @@ struct ni_module {
   NiLargePlan large{};       // kernel-class specific launch plan (CTA-per-trajectory)
   cudaLibrary_t lib = nullptr;  // NVRTC modules only
   std::string log;
+  std::string rhs_src;          // thread-per-trajectory modules: definition of `NiUserRhs` (recompiled with a user
+                                // predicate by ni_ensemble_ff2cond_user)
 };
+
+static const char *builtin_functor(int rhs_id) {
+  switch (rhs_id) {
+    case NI_RHS_HARMONIC: return "NiRhsHarmonic";
+    case NI_RHS_LORENZ63: return "NiRhsLorenz63";
+    case NI_RHS_VANDERPOL: return "NiRhsVanDerPol";
+    case NI_RHS_EXPONENTIAL: return "NiRhsExponential<1>";
+    case NI_RHS_RICCATI: return "NiRhsRiccati";
+    case NI_RHS_README_ADV: return "NiRhsReadmeAdvanced";
+    case NI_RHS_BLOWUP: return "NiRhsBlowup";
+    default: return nullptr;
+  }
+}
 
 static const NiKernelSet *builtin_small(int rhs_id, int n) {
   switch (rhs_id) {
@@ -103,6 +119,7 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module 
     m->k_init = ks->init[method];
     m->k_run[0] = ks->run[method][scipy ? 2 : advanced][0][fast];
     m->k_run[1] = ks->run[method][scipy ? 2 : advanced][1][fast];
+    m->rhs_src = std::string("#include \"ni_rhs_builtin.cuh\"\nusing NiUserRhs = ") + builtin_functor(rhs_id) + ";\n";
     *out = m;
     return NI_OK;
   }
@@ -173,9 +190,9 @@ static int load_nvrtc() {
 static int compile_and_load(const std::string &src, const char *nvrtc_options, const char *const names[3], ni_module *m) {
   if (int rc = load_nvrtc()) return rc;
   nvrtcProgram prog = nullptr;
-  const char *hdr_src[] = {ni_core_source, ni_math_source, ni_large_source};
-  const char *hdr_name[] = {"ni_core.cuh", "ni_math.cuh", "ni_large.cuh"};
-  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 3, hdr_src, hdr_name);
+  const char *hdr_src[] = {ni_core_source, ni_math_source, ni_large_source, ni_rhs_builtin_source};
+  const char *hdr_name[] = {"ni_core.cuh", "ni_math.cuh", "ni_large.cuh", "ni_rhs_builtin.cuh"};
+  int rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "ni_user_rhs.cu", 4, hdr_src, hdr_name);
   if (rc) return fail(NI_ERR_NVRTC, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(rc));
   std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
   if (nvrtc_options && *nvrtc_options) {  // space separated extra options
@@ -235,15 +252,15 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST | NI_MODE_SCIPY)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
   const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0,
             scipy = (mode & NI_MODE_SCIPY) ? 1 : 0;
-  std::string src;
-  src += "#include \"ni_core.cuh\"\n";
-  src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
-         ", Q = " + std::to_string(Q) + ";\n";
-  src += "  template <bool FAST>\n";
-  src += "  NI_DEV static void eval(double t, const double* y, const double* p, double* dy, double* aux) {\n";
-  src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
-  src += rhs_body;
-  src += "\n  }\n};\n";
+  std::string rhs_src;
+  rhs_src += "struct NiUserRhs {\n  static constexpr int N = " + std::to_string(n) + ", P = " + std::to_string(P) +
+             ", Q = " + std::to_string(Q) + ";\n";
+  rhs_src += "  template <bool FAST>\n";
+  rhs_src += "  NI_DEV static void eval(double t, const double* y, const double* p, double* dy, double* aux) {\n";
+  rhs_src += "    (void)t; (void)y; (void)p; (void)dy; (void)aux;\n";
+  rhs_src += rhs_body;
+  rhs_src += "\n  }\n};\n";
+  std::string src = "#include \"ni_core.cuh\"\n" + rhs_src;
   const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = scipy ? "2" : advanced ? "1" : "0",
                     F = fast ? "true" : "false";
   src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { "
@@ -262,6 +279,7 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   }
   m->fast = fast;
   m->scipy = scipy;
+  m->rhs_src = rhs_src;
   m->kind = NI_KIND_SMALL;
   m->n = n;
   m->P = P;
@@ -372,6 +390,11 @@ struct ni_ensemble {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t n_launches = 0;
   bool have_init_t = false, have_run_t = false;
+  struct CondKernels {
+    cudaLibrary_t lib = nullptr;
+    const void *k_run[2] = {nullptr, nullptr};
+  };
+  std::vector<std::pair<std::string, CondKernels>> cond_cache;  // user predicates compiled for this ensemble
 };
 
 template <class T>
@@ -406,6 +429,8 @@ NI_API int ni_ensemble_destroy(ni_ensemble *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->allocs) cudaFree(p);
+  for (auto &c : e->cond_cache)
+    if (c.second.lib) cudaLibraryUnload(c.second.lib);
   if (e->scratch) cudaFree(e->scratch);
   for (auto &ev : e->ev)
     if (ev) cudaEventDestroy(ev);
@@ -742,6 +767,74 @@ NI_API int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double 
     if (!dst) {
       tmp.resize((size_t)e->N);
       dst = tmp.data();
+    }
+    CU(cudaMemcpyAsync(dst, e->a.cond_hit, (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (n_hit) {
+      int64_t c = 0;
+      for (int64_t i = 0; i < e->N; ++i) c += dst[i] != 0;
+      *n_hit = c;
+    }
+  }
+  return NI_OK;
+}
+
+// ni.ff2cond with a user predicate: the body of
+//   __device__ bool cond(double t, const double* y, const double* aux, const double* cp)
+// is compiled (NVRTC) into a copy of this ensemble's run kernel and evaluated after every accepted step.
+NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const double *cond_params, int n_params,
+                                    uint8_t *hit, int64_t *n_hit) {
+  if (!e || !cond_body) return fail(NI_ERR_INVALID, "ensemble / cond_body is NULL");
+  if (n_params < 0 || n_params > 8 || (n_params > 0 && !cond_params)) return fail(NI_ERR_INVALID, "a predicate takes 0..8 parameters");
+  if (e->mod.kind != NI_KIND_SMALL || e->mod.rhs_src.empty())
+    return fail(NI_ERR_UNSUPPORTED, "user predicates are implemented for the thread-per-trajectory kernels only");
+  CU(cudaSetDevice(e->device));
+  ni_ensemble::CondKernels *ck = nullptr;
+  for (auto &c : e->cond_cache)
+    if (c.first == cond_body) ck = &c.second;
+  if (!ck) {
+    const ni_module &m = e->mod;
+    const std::string M = m.method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = m.scipy ? "2" : m.advanced ? "1" : "0",
+                      F = m.fast ? "true" : "false";
+    std::string src = "#define NI_HAVE_USER_COND 1\n#include \"ni_core.cuh\"\n" + m.rhs_src;
+    src += "__device__ __forceinline__ bool ni_user_cond(double t, const double* y, const double* aux, const double* cp) {\n";
+    src += "  (void)t; (void)y; (void)aux; (void)cp;\n";
+    src += cond_body;
+    src += "\n}\n";
+    src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK) ni_user_init(const NiArgs a) { (void)a; }\n";
+    src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run(const NiArgs a) { "
+           "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false, " + F + ">(a); }\n";
+    src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
+           "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true, " + F + ">(a); }\n";
+    ni_module tmp;
+    const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
+    const std::string opts = m.fast ? "--fmad=true" : "--fmad=false";
+    if (int rc = compile_and_load(src, opts.c_str(), names, &tmp)) return rc;
+    ni_ensemble::CondKernels k;
+    k.lib = tmp.lib;
+    k.k_run[0] = tmp.k_run[0];
+    k.k_run[1] = tmp.k_run[1];
+    e->cond_cache.emplace_back(std::string(cond_body), k);
+    ck = &e->cond_cache.back().second;
+  }
+  CU(cudaMemsetAsync(e->a.cond_hit, 0, (size_t)e->N, e->stream));
+  e->a.cond_kind = 5;
+  for (int i = 0; i < 8; ++i) e->a.cond_params[i] = i < n_params ? cond_params[i] : 0.0;
+  const void *saved[2] = {e->mod.k_run[0], e->mod.k_run[1]};
+  e->mod.k_run[0] = ck->k_run[0];
+  e->mod.k_run[1] = ck->k_run[1];
+  int64_t unfinished = 0;
+  int rc = ni_ensemble_run(e, &unfinished);
+  e->mod.k_run[0] = saved[0];
+  e->mod.k_run[1] = saved[1];
+  e->a.cond_kind = 0;
+  if (rc != NI_OK) return rc;
+  if (hit || n_hit) {
+    std::vector<uint8_t> tmpv;
+    uint8_t *dst = hit;
+    if (!dst) {
+      tmpv.resize((size_t)e->N);
+      dst = tmpv.data();
     }
     CU(cudaMemcpyAsync(dst, e->a.cond_hit, (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));

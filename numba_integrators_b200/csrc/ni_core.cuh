@@ -25,6 +25,8 @@
 // chains in dgemv order, every element-wise expression is unfused
 // (__dmul_rn/__dadd_rn are never contracted, whatever -fmad says).
 #pragma once
+#ifndef NI_CORE_CUH
+#define NI_CORE_CUH
 
 #define NI_RK23 0
 #define NI_RK45 1
@@ -88,10 +90,11 @@ struct NiArgs {
   unsigned int *rec_traj, *rec_step;
   double *rec_t, *rec_y, *rec_aux;  // rec_y [n][rec_cap], rec_aux [Q][rec_cap]
   // ff2cond: built-in predicate parameters
-  int cond_kind;                // 0 none, 1 y[i] > c, 2 y[i] < c, 3 aux[i] > c, 4 aux[i] < c
+  int cond_kind;                // 0 none, 1 y[i] > c, 2 y[i] < c, 3 aux[i] > c, 4 aux[i] < c, 5 user predicate (NVRTC)
   int cond_index;
   double cond_value;
   unsigned char *cond_hit;
+  double cond_params[8];        // cond_kind == 5: parameters of the user predicate
 };
 
 // Arithmetic policy.  Strict (FAST = false): every element-wise expression is evaluated unfused, as numba
@@ -349,9 +352,19 @@ NI_DEV double ni_ulp_eps(double t, double dir) {
 }
 
 // ---------------------------------------------------------------- predicates (ff2cond)
+#ifdef NI_HAVE_USER_COND
+// user predicate of ff2cond, defined by the generated translation unit after this header
+__device__ __forceinline__ bool ni_user_cond(double t, const double *y, const double *aux, const double *cp);
+#endif
+
 template <int n, int Q>
-NI_DEV bool ni_cond_test(const NiArgs &a, const double (&y)[n], const double *aux) {
+NI_DEV bool ni_cond_test(const NiArgs &a, double t, const double (&y)[n], const double *aux) {
   if (a.cond_kind == 0) return false;
+#ifdef NI_HAVE_USER_COND
+  if (a.cond_kind == 5) return ni_user_cond(t, y, aux, a.cond_params);
+#else
+  (void)t;
+#endif
   double v = 0.0;
   if (a.cond_kind <= 2) {
 #pragma unroll
@@ -726,7 +739,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       if (REC && park && !sp_fail) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
       if (fail || (act && sp_fail)) status = NI_ST_FAILED;
       if (nan) status = NI_ST_NONFINITE;
-      if (a.cond_kind != 0 && accepted && ni_cond_test<n, Q>(a, y, aux)) {
+      if (a.cond_kind != 0 && accepted && ni_cond_test<n, Q>(a, t, y, aux)) {
         a.cond_hit[idx] = 1;
         parked = true;
         done = true;
@@ -755,3 +768,4 @@ template <class Rhs, int METHOD, int SEM, bool REC, bool FAST>
 __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(Rhs::N)) ni_k_run(const NiArgs a) {
   ni_small_run_body<Rhs, METHOD, SEM, REC, FAST>(a);
 }
+#endif  // NI_CORE_CUH

@@ -18,6 +18,8 @@
 // uses a tree order (the reference's own n >= 4 order is host-BLAS/LLVM dependent, SURVEY.md
 // appendix B, so parity for n >= 4 is 1e-12 relative + identical step counts, not bitwise).
 #pragma once
+#ifndef NI_LARGE_CUH
+#define NI_LARGE_CUH
 #include "ni_core.cuh"
 
 
@@ -437,3 +439,4 @@ __global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ni_k_large_run(const 
   extern __shared__ double ni_smem[];
   ni_large_run_body<Rhs, METHOD, ADV, REC, CPT>(a, ni_smem);
 }
+#endif  // NI_LARGE_CUH

@@ -6,6 +6,8 @@
 // same as in oracle/ni_oracle.c:rhs_eval and in the numba functions oracle/gen_golden.py
 // hands to the reference, so that all three produce identical bits.
 #pragma once
+#ifndef NI_RHS_BUILTIN_CUH
+#define NI_RHS_BUILTIN_CUH
 #include "ni_core.cuh"
 
 #define NI_RHS_HARMONIC 0
@@ -98,3 +100,4 @@ struct NiRhsBlowup {
     dy[0] = NiA<FAST>::mul(y[0], y[0]);
   }
 };
+#endif  // NI_RHS_BUILTIN_CUH

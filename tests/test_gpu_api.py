@@ -346,3 +346,33 @@ def test_structref_flavour():  # ni.sr (_structref.py): x / x_bound field names,
         assert state.x == g['rec_t'][0, k] and np.array_equal(state.y, g['rec_y'][0, k])
         k += 1
     assert k == g['n_accepted'][0] == 10 and state.x == state.x_bound == 0.0
+
+
+def test_ff2cond_with_user_predicates_on_an_ensemble():
+    """ff2cond with (a) a Python predicate translated into the kernel, (b) a CUDA predicate snippet, (c) the
+    built-in threshold: all stop every trajectory at the same accepted step as the reference's host loop."""
+    rng = np.random.default_rng(2)
+    y0 = rng.uniform(0.5, 1.5, size=(500, 1))
+
+    def condition(solver, parameters):                          # test_public.py:145-147
+        return solver.y[0] > parameters
+
+    T = 1.6                                                     # exp(1.6) = 4.95: only y0 > 0.81 crosses 4
+    ens = {k: ni.RK45(ni.rhs.exponential, 0.0, y0, T, rtol=1e-6, atol=1e-8) for k in 'abc'}
+    hit_a = ni.ff2cond(ens['a'], condition, 4.0)
+    hit_b = ni.ff2cond(ens['b'], ni.CudaCondition('return y[0] > cp[0];'), 4.0)
+    hit_c = ni.ff2cond(ens['c'], ni.y_above(0), 4.0)
+    assert np.array_equal(hit_a, hit_b) and np.array_equal(hit_a, hit_c) and 0 < hit_a.sum() < 500
+    for k in 'bc':
+        assert np.array_equal(ens['a'].t, ens[k].t) and np.array_equal(ens['a'].y, ens[k].y)
+    y, t = ens['a'].y[:, 0], ens['a'].t
+    assert np.all(y[hit_a] > 4.0) and np.all(t[~np.asarray(hit_a)] == T) and np.all(t[hit_a] <= T)
+    # the host loop of the reference gives the same stopping point for a single trajectory
+    one = ni.RK45(ni.rhs.exponential, 0.0, y0[7], T, rtol=1e-6, atol=1e-8)
+    while one.step():
+        if one.y[0] > 4.0:
+            break
+    assert one.t == t[7] and one.y[0] == y[7]
+    # a second ff2cond continues from the stopping points
+    hit2 = ni.ff2cond(ens['a'], condition, 4.5)
+    assert 0 < hit2.sum() < hit_a.sum() and np.all(ens['a'].y[:, 0][hit2] > 4.5)

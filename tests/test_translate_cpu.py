@@ -105,3 +105,21 @@ def test_unsupported_constructs_are_named():
         ni.translate(wrong_len, 2)
     with pytest.raises(ni.TranslationError, match='parameters'):
         ni.translate(f_lorenz, 3, None, True)
+
+
+def condition_exponential(solver, parameters):  # tests/unittests/test_public.py:145-147 of the reference
+    return solver.y[0] > parameters
+
+
+def condition_combo(solver, p):
+    r2 = solver.y[0] ** 2 + solver.y[1] ** 2
+    return (r2 < p[0] and solver.t > p[1]) or solver.auxiliary[0] >= 3.0
+
+
+def test_predicate_translation():
+    body, cp = ni.translate_condition(condition_exponential, 1, parameters=4.0)
+    assert 'return (y[0] > cp[0]);' in body and cp.tolist() == [4.0]
+    body, cp = ni.translate_condition(condition_combo, 2, Q=1, parameters=np.array((0.5, 1.0)))
+    assert '&&' in body and '||' in body and 'aux[0]' in body and cp.tolist() == [0.5, 1.0]
+    with pytest.raises(ni.TranslationError, match='solver.h_abs'):
+        ni.translate_condition(lambda solver, p: solver.h_abs > p, 1, parameters=1.0)
