@@ -190,6 +190,12 @@ class _Translator:
             a, b = self.expr(node.left), self.expr(node.right)
             if isinstance(node.op, ast.Pow):
                 return self.power(node, a, b)
+            if isinstance(node.op, (ast.Mod, ast.FloorDiv)):
+                if isinstance(a, (int, float)) and isinstance(b, (int, float)):  # index arithmetic on loop counters
+                    return a % b if isinstance(node.op, ast.Mod) else a // b
+                if isinstance(node.op, ast.Mod):  # Python's float %: result has the sign of the divisor
+                    return self.broadcast(lambda x, y: f'({x} - floor({x} / {y}) * {y})', a, b)
+                return self.broadcast(lambda x, y: f'floor({x} / {y})', a, b)
             if type(node.op) in _BINOPS:
                 op = _BINOPS[type(node.op)]
                 if isinstance(a, (int, float)) and isinstance(b, (int, float)):  # constant folding as Python does

@@ -36,7 +36,7 @@
 #define NI_ST_FAILED 2     // step size fell below 8 ulp(t)   (_basic.py:179-180)
 #define NI_ST_NONFINITE 3  // error norm is NaN (the reference would spin forever)
 
-#define NI_MAX_SMALL_N 16
+#define NI_MAX_SMALL_N 64
 #ifndef NI_BLOCK
 #define NI_BLOCK 128
 #endif

@@ -376,3 +376,25 @@ def test_ff2cond_with_user_predicates_on_an_ensemble():
     # a second ff2cond continues from the stopping points
     hit2 = ni.ff2cond(ens['a'], condition, 4.5)
     assert 0 < hit2.sum() < hit_a.sum() and np.all(ens['a'].y[:, 0][hit2] > 4.5)
+
+
+def test_dense_medium_dimension_python_rhs_against_scipy():
+    """n = 40 densely coupled system through the Python-source translator (stage vectors spill from registers
+    to local memory above n ~ 16 -- slower, same results): compared with SciPy at tolerance level."""
+    import scipy.integrate
+    n = 40
+
+    def ring(t, y):
+        dy = np.zeros(40)
+        m = np.sum(y) / 40
+        for j in range(40):
+            dy[j] = -0.5 * (y[j] - m) + 0.1 * np.sin(y[(j + 1) % 40] - y[j]) + 0.05 * np.cos(t)
+        return dy
+
+    rng = np.random.default_rng(9)
+    y0 = rng.uniform(-1, 1, size=(33, n))
+    ens = ni.RK45(ring, 0.0, y0, 4.0, rtol=1e-9, atol=1e-11)
+    assert ens.run() == 0 and np.all(ens.t == 4.0)
+    for i in (0, 17, 32):
+        ref = scipy.integrate.solve_ivp(ring, (0.0, 4.0), y0[i], method='RK45', rtol=1e-11, atol=1e-13)
+        assert np.max(np.abs(ens.y[i] - ref.y[:, -1])) < 1e-7
