@@ -1,8 +1,12 @@
-"""The reference's own functional tests (tests/unittests/test_public.py), restated line by line against this
-package: same problems (reference.py:38-57, as Python lambdas that go through the source translator), same
-tolerances, same assertions, SciPy as the comparison oracle exactly as the reference uses it."""
-from itertools import product
+"""What the reference's functional tests pin (tests/unittests/test_public.py), checked on the GPU path with plain
+Python right-hand sides going through the source translator and SciPy as the comparison solver, as upstream does:
 
+  * accuracy against the analytic solution no worse than 1.02 x SciPy's at rtol = atol = 1e-10, and landing exactly
+    on t_bound                                                                    (test_public.py:17-46)
+  * every step obeys max_step*(1 - 1e-13) < dt <= max_step                         (:48-61, :127-142)
+  * Advanced and basic solvers give identical t, y at every step                   (:79-125)
+  * ff2t lands on t_end and restores t_bound; ff2cond stops at the first hit        (:150-175)
+"""
 import numpy as np
 import pytest
 import scipy.integrate
@@ -11,124 +15,83 @@ import numba_integrators_b200 as ni
 
 pytestmark = pytest.mark.gpu
 
-
-class Problem:  # reference.py:18-33
-    problems = []
-
-    def __init__(self, name, differential, solution, x0, x_end):
-        self.name, self.differential, self.solution, self.x0, self.x_end = name, differential, solution, x0, x_end
-        self.y0, self.y_end = solution(x0), solution(x_end)
-        Problem.problems.append(self)
-
-
-riccati = Problem('riccati', lambda x, y: 2 * y/x - x ** 2 * y ** 2,
-                  lambda x: np.array((x**2 / (x**5 + 4) * 5,), np.float64), 1., 20.)
-sine = Problem('sine', lambda x, y: np.array((y[1], -y[0])),
-               lambda x: np.array((np.sin(x), np.cos(x)), np.float64), 0., 10.)
-exponential = Problem('exponential', lambda x, y: y,
-                      lambda x: np.array((np.exp(x),), np.float64), 0., 10.)
-scipy_integrators = {ni.RK23: scipy.integrate.RK23, ni.RK45: scipy.integrate.RK45}
+# the three initial-value problems of reference.py:38-57: (rhs, exact solution, x0, x_end)
+IVPS = {
+    'riccati': (lambda x, y: 2 * y/x - x ** 2 * y ** 2, lambda x: np.array([x**2 / (x**5 + 4) * 5]), 1.0, 20.0),
+    'sine': (lambda x, y: np.array((y[1], -y[0])), lambda x: np.array([np.sin(x), np.cos(x)]), 0.0, 10.0),
+    'exponential': (lambda x, y: y, lambda x: np.array([np.exp(x)]), 0.0, 10.0),
+}
+SCIPY = {'RK23': scipy.integrate.RK23, 'RK45': scipy.integrate.RK45}
 
 
-def scipy_solve(solver_type, function, x0, y0, x_end, rtol, atol):  # reference.py:64-77
-    solver = scipy_integrators[solver_type](function, x0, y0, x_end, atol=atol, rtol=rtol)
-    while solver.status == 'running':
-        solver.step()
-    assert solver.t == x_end
-    return solver.y
+def exp_solver(ctor=None, **kw):
+    rhs, exact, x0, x_end = IVPS['exponential']
+    return (ctor or ni.RK45)(rhs, x0, exact(x0), x_end, **kw), x_end
 
 
-def compare_to_scipy(solver_type, rtol, atol, problem):  # test_public.py:17-38
-    solver = solver_type(problem.differential, problem.x0, problem.y0, problem.x_end, rtol=rtol, atol=atol)
-    while ni.step(solver):
+@pytest.mark.parametrize('method', ['RK23', 'RK45'])
+@pytest.mark.parametrize('name', list(IVPS))
+def test_accuracy_relative_to_scipy(method, name):
+    rhs, exact, x0, x_end = IVPS[name]
+    tol = 1e-10
+    ours = getattr(ni, method)(rhs, x0, exact(x0), x_end, rtol=tol, atol=tol)
+    while ni.step(ours):
         pass
-    assert solver.t == problem.x_end
-    y_ni = solver.y
-    err_ni = np.sum(np.abs(y_ni - problem.y_end))
-    y_scipy = scipy_solve(solver_type, problem.differential, problem.x0, problem.y0, problem.x_end, rtol, atol)
-    err_scipy = np.sum(np.abs(y_scipy - problem.y_end))
-    assert err_ni < err_scipy*1.02
+    assert ours.t == x_end
+    theirs = SCIPY[method](rhs, x0, exact(x0), x_end, rtol=tol, atol=tol)
+    while theirs.status == 'running':
+        theirs.step()
+    err_ours, err_scipy = np.abs(ours.y - exact(x_end)).sum(), np.abs(theirs.y - exact(x_end)).sum()
+    assert err_ours < 1.02 * err_scipy, (err_ours, err_scipy)
 
 
-class Test_Basic:
-    @pytest.mark.parametrize(('solver', 'problem'), product(ni.ALL, Problem.problems),
-                             ids=lambda v: getattr(v, 'name', getattr(v, '__name__', str(v))))
-    def test_to_scipy(self, solver, problem):  # :42-46
-        compare_to_scipy(solver, 1e-10, 1e-10, problem)
-
-    def test_max_step(self):  # :48-61
-        max_step = 1e-4
-        low = max_step * (1 - 1e-13)
-        problem = exponential
-        solver = ni.RK45(problem.differential, problem.x0, problem.y0, t_bound=problem.x_end, first_step=max_step,
-                         max_step=max_step)
-        x_prev = solver.t
-        for _ in range(100):
-            ni.step(solver)
-            assert low < (solver.t - x_prev) <= max_step
-            x_prev = solver.t
+@pytest.mark.parametrize('first_step', [1e-4, 0.0])
+def test_max_step_is_strict(first_step):
+    max_step = 1e-4
+    solver, _ = exp_solver(max_step=max_step, first_step=first_step)
+    previous = solver.t
+    for _ in range(100):
+        ni.step(solver)
+        assert max_step * (1 - 1e-13) < solver.t - previous <= max_step
+        previous = solver.t
 
 
-def f_advanced(t, y, p):  # test_public.py:65-67 (the inner call inlined: a translated RHS cannot call other functions)
-    return y, p
+def test_advanced_factory_returns_dict_for_all():
+    assert isinstance(ni.Advanced(None, None, ni.Solvers.ALL), dict)
 
 
-class Test_Advanced:
-    parameters = (1., np.array((1., 1.), dtype=np.float64))
-
-    def test_all_class_creation(self):  # :75-77
-        Solvers = ni.Advanced(None, None, ni.Solvers.ALL)
-        assert isinstance(Solvers, dict)
-
-    @pytest.mark.parametrize('solver_type', (ni.RK23, ni.RK45))
-    def test_identical_to_base(self, solver_type):  # :79-125
-        problem = exponential
-        solver_base = solver_type(problem.differential, problem.x0, problem.y0, problem.x_end)
-        Solvers = ni.Advanced(None, None, solver_type)
-        assert Solvers is not None
-        assert not isinstance(Solvers, dict)
-        solver_advanced = Solvers(f_advanced, problem.x0, problem.y0, self.parameters, problem.x_end)
-        # the auxiliary round-trips the (float, array) parameter tuple -- flattened to (1, 1, 1) here
-        assert np.array_equal(solver_advanced.auxiliary, [1., 1., 1.])
-        assert solver_base.t == solver_advanced.t
-        assert np.all(solver_base.y == solver_advanced.y)
-        ni.step(solver_base)
-        ni.step(solver_advanced)
-        assert solver_base.t == solver_advanced.t
-        assert np.all(solver_base.y == solver_advanced.y)
-        assert np.array_equal(solver_advanced.auxiliary, [1., 1., 1.])
-        x_base, y_base, x_advanced, y_advanced = [], [], [], []
-        while ni.step(solver_base):
-            assert ni.step(solver_advanced)
-            x_base.append(solver_base.t)
-            y_base.append(solver_base.y)
-            x_advanced.append(solver_advanced.t)
-            y_advanced.append(solver_advanced.y)
-        assert x_base == x_advanced
-        assert all(np.all(y_b == y_a) for y_b, y_a in zip(y_base, y_advanced))
+@pytest.mark.parametrize('ctor', [ni.RK23, ni.RK45])
+def test_advanced_is_bitwise_identical_to_basic(ctor):
+    def rhs_with_parameters(t, y, p):      # upstream wraps the basic RHS and hands the parameters back as auxiliary
+        return y, p
+    parameters = (1.0, np.array((1.0, 1.0)))
+    basic, x_end = exp_solver(ctor)
+    advanced = ni.Advanced(None, None, ctor)(rhs_with_parameters, 0.0, basic.y, parameters, x_end)
+    assert not isinstance(ni.Advanced(None, None, ctor), dict)
+    assert np.array_equal(advanced.auxiliary, [1.0, 1.0, 1.0])          # the (float, array) tuple, flattened
+    assert (basic.t, basic.y.tolist()) == (advanced.t, advanced.y.tolist())
+    n = 0
+    while ni.step(basic):
+        assert ni.step(advanced)
+        assert basic.t == advanced.t and np.array_equal(basic.y, advanced.y)
+        n += 1
+    assert n > 5 and not ni.step(advanced)
+    assert np.array_equal(advanced.auxiliary, [1.0, 1.0, 1.0])
 
 
-def condition_exponential(solver, parameters):  # :145-147
-    return solver.y[0] > parameters
+def test_fast_forward_to_time():
+    solver, x_end = exp_solver()
+    leg = x_end / 10.1
+    assert ni.ff2t(solver, leg)
+    assert solver.t == leg and solver.t_bound == x_end
+    while ni.ff2t(solver, solver.t + leg):
+        pass
+    assert solver.t == solver.t_bound == x_end
 
 
-class Test_fast_forward:
-    def test_t(self):  # :150-165
-        problem = exponential
-        solver = ni.RK45(problem.differential, problem.x0, problem.y0, problem.x_end)
-        t_range = problem.x_end - problem.x0
-        t_step1 = t_range / 10.1
-        ni.ff2t(solver, t_step1)
-        assert solver.t == t_step1
-        assert solver.t_bound == problem.x_end
-        while ni.ff2t(solver, solver.t + t_step1):
-            ...
-        assert solver.t == solver.t_bound
-        assert solver.t_bound == problem.x_end
-
-    def test_condition(self):  # :167-175
-        problem = exponential
-        solver = ni.RK45(problem.differential, problem.x0, problem.y0, problem.x_end)
-        condition_parameter = 4.
-        assert ni.ff2cond(solver, condition_exponential, condition_parameter)
-        assert condition_exponential(solver, condition_parameter)
+def test_fast_forward_to_condition():
+    def y0_above(solver, threshold):
+        return solver.y[0] > threshold
+    solver, _ = exp_solver()
+    assert ni.ff2cond(solver, y0_above, 4.0)
+    assert y0_above(solver, 4.0)
