@@ -398,3 +398,25 @@ def test_dense_medium_dimension_python_rhs_against_scipy():
     for i in (0, 17, 32):
         ref = scipy.integrate.solve_ivp(ring, (0.0, 4.0), y0[i], method='RK45', rtol=1e-11, atol=1e-13)
         assert np.max(np.abs(ens.y[i] - ref.y[:, -1])) < 1e-7
+
+
+def test_attempt_budget_relaunch_and_non_finite_inputs():
+    """(a) A per-launch attempt budget (bounded kernel time) parks trajectories between attempts and relaunches:
+    bit-identical to the unbounded run, also mid-retry.  (b) NaN in the state latches NI_ST_NONFINITE instead of
+    spinning forever like the reference's retry loop would."""
+    from numba_integrators_b200 import _lib, workloads as wl
+    w = wl.c3_lorenz(N=3000, t_bound=2.0)
+    make = lambda: ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 2.0, rtol=1e-8, atol=1e-8)  # noqa: E731
+    a, b = make(), make()
+    _lib.check(_lib.lib().ni_ensemble_set_max_attempts(b._h, 37))
+    assert a.run() == 0 and b.run() == 0
+    assert b.timing()['launches'] > a.timing()['launches'] + 3
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.n_accepted, b.n_accepted)
+    assert np.array_equal(a.n_rejected, b.n_rejected) and np.array_equal(a.h_abs, b.h_abs)
+    y0 = w.y0[:64].copy()
+    y0[5, 1] = np.nan
+    c = ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, y0, w.params[:64], 1.0, rtol=1e-8, atol=1e-8)
+    assert c.run() == 0
+    st = c.status
+    assert st[5] == 3 and np.all(np.delete(st, 5) == 1)
+    assert not np.any(ni.step(c))
