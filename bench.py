@@ -370,10 +370,13 @@ def main():
                                    'nominal 37.2 TFLOP/s)',
                     'hbm_gbs_measured': peaks.get('hbm_gbs')}
         try:  # DRAM traffic of this kernel measured by ncu (profiles/), scaled to this launch's trajectory count
-            tr = json.loads((ROOT / 'profiles' / 'r01_dram_traffic.json').read_text()).get(args.workload)
+            key = args.workload + ('_fast' if args.arithmetic == 'fast' else '')
+            tr = json.loads((ROOT / 'profiles' / 'r01_dram_traffic.json').read_text()).get(key)
             if tr:
                 roofline['traffic'] = tr['bytes_per_trajectory'] * N
                 roofline['traffic_source'] = tr['capture']
+                if 'fp64_pipe_busy' in tr:  # ncu: fraction of cycles the FP64 pipe was busy (same capture)
+                    roofline['fp64_pipe_busy_ncu'] = tr['fp64_pipe_busy']
                 roofline['algorithmic_bytes'] = (N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13)
                                                  + (w.record_bytes_per_step * acc_rank if record else 0))
         except (OSError, ValueError):
