@@ -401,6 +401,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             rate, k, threads, dt = cpu_oracle_rate(w, args.cpu_seconds)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                    'note': 'C port of the reference algorithm (the reference itself is Python + numba and '
+                                            'cannot travel to the GPU box; it measured 0.27-0.44 M steps/s/thread in '
+                                            'BASELINE.md section 2, the port runs ~7 M steps/s/thread)',
                                     'sample': f'first {k} trajectories of the same workload, {dt:.1f} s, oracle C port '
                                               f'of the reference algorithm on {threads} host threads'}
         print(json.dumps(line))
