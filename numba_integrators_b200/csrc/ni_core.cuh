@@ -499,7 +499,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   const int max_acc = a.max_accepts > 0x7fffffffLL ? 0x7fffffff : (int)a.max_accepts;
 
   long long idx = 0;
-  bool active = false, exhausted = false, need = true, fresh = true, last_accept = false, parked = false, srej = false;
+  bool active = false, exhausted = false, need = true, last_accept = false, parked = false, srej = false;
   double t = 0, h_abs = 0, tb = 0, dir = 1, step_h = 0;
   double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
 #pragma unroll
@@ -578,7 +578,6 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           nrej = a.n_rej[idx];
           att_left = max_att;
           acc_left = max_acc;
-          fresh = true;
           last_accept = false;
           parked = false;
           srej = SP ? a.step_rejected[idx] != 0 : false;
@@ -597,7 +596,8 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     const double eps = ni_ulp_eps(t, dir);
     const double min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);  // scipy: 10 ulp
     if (SP) {
-      if (fresh) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
+      // first attempt of a step <=> no rejection seen in it yet (also right after resuming a parked trajectory)
+      if (!srej) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
     } else {
       h_abs = h_abs < min_step ? min_step : h_abs;
     }
@@ -719,7 +719,6 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       nrej += (upd && !ok) ? 1 : 0;
       acc_left -= accepted ? 1 : 0;
       att_left -= upd ? 1 : 0;
-      fresh = accepted ? true : (upd ? false : fresh);
       last_accept = act ? accepted : last_accept;
       srej = upd ? !ok : srej;
       if (REC && accepted) {
