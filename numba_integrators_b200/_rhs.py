@@ -21,6 +21,7 @@ _BUILTIN_SHAPE = {'harmonic': (2, 0, 0), 'sine': (2, 0, 0), 'lorenz63': (3, 3, 1
 
 class RHS:
     """Base: `n` state dimension (None = taken from y0), `P` parameters, `Q` auxiliary outputs."""
+    shared_module = False  # True: the module handle is cached for the process and must not be destroyed by a solver
     name = '?'
     n = None
     P = 0
@@ -58,6 +59,16 @@ class BuiltinRHS(RHS):
         return f'BuiltinRHS({self.name!r})'
 
 
+_MODULE_CACHE = {}  # (kind, body, n, P, Q, method, mode, options) -> module handle; lives for the process
+
+
+def _cached_module(key, make):
+    """NVRTC specialisations cost 1-10 s: share them between solvers built from the same source."""
+    if key not in _MODULE_CACHE:
+        _MODULE_CACHE[key] = make()
+    return _MODULE_CACHE[key]
+
+
 class CudaRHS(RHS):
     """User right-hand side: the body of
 
@@ -65,6 +76,8 @@ class CudaRHS(RHS):
 
     in CUDA C++.  It is fused into the RK stage loop at load time with NVRTC (sm_100a).
     """
+
+    shared_module = True
 
     def __init__(self, body, n, P=0, Q=0, parameters=None, name='user', nvrtc_options=''):
         self.body, self.n, self.P, self.Q, self.name = str(body), int(n), int(P), int(Q), name
@@ -74,10 +87,12 @@ class CudaRHS(RHS):
     def _module(self, n, method, mode):
         if n != self.n:
             raise ValueError(f'y0 has {n} components, the RHS was declared with n={self.n}')
-        out = _lib._vp()
-        _lib.check(_lib.lib().ni_module_compile(self.body.encode(), self.n, self.P, self.Q, int(method),
-                                                int(mode), self.nvrtc_options.encode(), out))
-        return out
+        def make():
+            out = _lib._vp()
+            _lib.check(_lib.lib().ni_module_compile(self.body.encode(), self.n, self.P, self.Q, int(method),
+                                                    int(mode), self.nvrtc_options.encode(), out))
+            return out
+        return _cached_module(('dense', self.body, self.n, self.P, self.Q, int(method), int(mode), self.nvrtc_options), make)
 
     def __repr__(self):
         return f'CudaRHS({self.name!r}, n={self.n}, P={self.P}, Q={self.Q})'
@@ -91,16 +106,20 @@ class CudaStencilRHS(RHS):
     returning dy_j from y_{j-1}, y_j, y_{j+1} (zero outside 0..n-1).  Fused into the CTA-per-trajectory
     kernels with NVRTC; n is taken from y0."""
 
+    shared_module = True
+
     def __init__(self, body, P=0, parameters=None, name='user_stencil', nvrtc_options=''):
         self.body, self.P, self.Q, self.n, self.name = str(body), int(P), 0, None, name
         self.nvrtc_options = nvrtc_options
         self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
 
     def _module(self, n, method, mode):
-        out = _lib._vp()
-        _lib.check(_lib.lib().ni_module_compile_stencil(self.body.encode(), int(n), self.P, int(method),
-                                                        int(mode), self.nvrtc_options.encode(), out))
-        return out
+        def make():
+            out = _lib._vp()
+            _lib.check(_lib.lib().ni_module_compile_stencil(self.body.encode(), int(n), self.P, int(method),
+                                                            int(mode), self.nvrtc_options.encode(), out))
+            return out
+        return _cached_module(('stencil', self.body, int(n), self.P, 0, int(method), int(mode), self.nvrtc_options), make)
 
     def __repr__(self):
         return f'CudaStencilRHS({self.name!r}, P={self.P})'

@@ -194,7 +194,8 @@ class Ensemble:
             self._L.ni_ensemble_destroy(self._h)
             self._h = None
         if getattr(self, '_mod', None):
-            self._L.ni_module_destroy(self._mod)
+            if not getattr(self.fun, 'shared_module', False):  # NVRTC modules are cached per process (_rhs.py)
+                self._L.ni_module_destroy(self._mod)
             self._mod = None
 
     def __del__(self):

@@ -6,6 +6,7 @@
 // fails with NI_ERR_CUDA when no CUDA device is usable.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstdarg>
 #include <cstdint>
@@ -186,8 +187,71 @@ static int load_nvrtc() {
   return NI_OK;
 }
 
+// ---- on-disk cubin cache (opt-in: NI_B200_CACHE_DIR): key = FNV-1a of source + headers + options + library version
+static uint64_t fnv1a(uint64_t h, const char *p, size_t n) {
+  for (size_t i = 0; i < n; ++i) h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+  return h;
+}
+static std::string cache_path(const std::string &src, const std::string &opts) {
+  const char *dir = getenv("NI_B200_CACHE_DIR");
+  if (!dir || !*dir) return std::string();
+  uint64_t h = 1469598103934665603ull;
+  h = fnv1a(h, src.data(), src.size());
+  h = fnv1a(h, opts.data(), opts.size());
+  for (const char *hdr : {ni_core_source, ni_math_source, ni_large_source, ni_rhs_builtin_source}) h = fnv1a(h, hdr, strlen(hdr));
+  char name[64];
+  snprintf(name, sizeof name, "/ni_b200_v%d_sm100a_%016llx.cubin", ni_version(), (unsigned long long)h);
+  return std::string(dir) + name;
+}
+static bool read_file(const std::string &path, std::vector<char> *out) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out->resize(n > 0 ? (size_t)n : 0);
+  const bool ok = n > 0 && fread(out->data(), 1, (size_t)n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+static void write_file_atomic(const std::string &path, const std::vector<char> &data) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (ok)
+    rename(tmp.c_str(), path.c_str());
+  else
+    remove(tmp.c_str());
+}
+
+static int load_cubin(const std::vector<char> &cubin, const char *const names[3], ni_module *m) {
+  cudaError_t ce = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  cudaKernel_t k[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaLibraryGetKernel(&k[i], m->lib, names[i]);
+  if (ce != cudaSuccess) {
+    int code = fail(NI_ERR_CUDA, "loading the compiled RHS module: %s", cudaGetErrorString(ce));
+    if (m->lib) cudaLibraryUnload(m->lib);
+    m->lib = nullptr;
+    return code;
+  }
+  m->k_init = (const void *)k[0];
+  m->k_run[0] = (const void *)k[1];
+  m->k_run[1] = (const void *)k[2];
+  return NI_OK;
+}
+
 // Compiles `src` (which includes the embedded kernel headers) for sm_100a and loads the three entry points.
 static int compile_and_load(const std::string &src, const char *nvrtc_options, const char *const names[3], ni_module *m) {
+  const std::string cpath = cache_path(src, nvrtc_options ? nvrtc_options : "");
+  if (!cpath.empty()) {
+    std::vector<char> cached;
+    if (read_file(cpath, &cached) && load_cubin(cached, names, m) == NI_OK) {
+      m->log = "cubin cache hit: " + cpath;
+      return NI_OK;
+    }
+  }
   if (int rc = load_nvrtc()) return rc;
   nvrtcProgram prog = nullptr;
   const char *hdr_src[] = {ni_core_source, ni_math_source, ni_large_source, ni_rhs_builtin_source};
@@ -223,19 +287,8 @@ static int compile_and_load(const std::string &src, const char *nvrtc_options, c
   std::vector<char> cubin(csz);
   g_nvrtc.GetCUBIN(prog, cubin.data());
   g_nvrtc.DestroyProgram(&prog);
-
-  cudaError_t ce = cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-  cudaKernel_t k[3] = {nullptr, nullptr, nullptr};
-  for (int i = 0; i < 3 && ce == cudaSuccess; ++i) ce = cudaLibraryGetKernel(&k[i], m->lib, names[i]);
-  if (ce != cudaSuccess) {
-    int code = fail(NI_ERR_CUDA, "loading the compiled RHS module: %s", cudaGetErrorString(ce));
-    if (m->lib) cudaLibraryUnload(m->lib);
-    m->lib = nullptr;
-    return code;
-  }
-  m->k_init = (const void *)k[0];
-  m->k_run[0] = (const void *)k[1];
-  m->k_run[1] = (const void *)k[2];
+  if (int rc = load_cubin(cubin, names, m)) return rc;
+  if (!cpath.empty()) write_file_atomic(cpath, cubin);
   return NI_OK;
 }
 

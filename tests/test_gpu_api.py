@@ -420,3 +420,26 @@ def test_attempt_budget_relaunch_and_non_finite_inputs():
     st = c.status
     assert st[5] == 3 and np.all(np.delete(st, 5) == 1)
     assert not np.any(ni.step(c))
+
+
+def test_module_caches(tmp_path, monkeypatch):
+    """NVRTC specialisations are shared per process, and cubins persist on disk when NI_B200_CACHE_DIR is set."""
+    import time
+    from numba_integrators_b200 import _lib, _rhs
+    monkeypatch.setenv('NI_B200_CACHE_DIR', str(tmp_path))
+    body = 'dy[0] = -y[0] * 1.2345;  /* cache test */'
+    t0 = time.perf_counter()
+    a = ni.RK45(ni.CudaRHS(body, n=1), 0.0, np.ones(1), 1.0)
+    t_cold = time.perf_counter() - t0
+    assert len(list(tmp_path.glob('*.cubin'))) == 1
+    n_modules = len(_rhs._MODULE_CACHE)
+    b = ni.RK45(ni.CudaRHS(body, n=1), 0.0, np.ones((5, 1)), 1.0)       # same source: in-process hit
+    assert len(_rhs._MODULE_CACHE) == n_modules and a._mod.value == b._mod.value
+    _rhs._MODULE_CACHE.clear()                                          # force a reload from the disk cache
+    t0 = time.perf_counter()
+    c = ni.RK45(ni.CudaRHS(body, n=1), 0.0, np.ones(1), 1.0)
+    t_warm = time.perf_counter() - t0
+    assert b'cubin cache hit' in _lib.lib().ni_module_log(c._mod)
+    assert t_warm < t_cold
+    a.run(), c.run()
+    assert a.y == c.y and abs(a.y[0] - np.exp(-1.2345)) < 1e-3
