@@ -98,6 +98,9 @@ static const NiKernelSet *builtin_small(int rhs_id, int n) {
   }
 }
 
+static int compile_stencil_module(const std::string &functor_src, int n, int P, int method, int mode,
+                                  const char *nvrtc_options, ni_module **out);
+
 NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -125,8 +128,12 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module 
     return NI_OK;
   }
   if ((fast || scipy) && (rhs_id == NI_RHS_HEAT1D || rhs_id == NI_RHS_BURGERS1D)) {
+    // the ahead-of-time library carries the reference-semantics strict kernels; the opt-in variants of the
+    // CTA-per-trajectory kernels are specialised with NVRTC from the same templates
     delete m;
-    return fail(NI_ERR_UNSUPPORTED, "NI_MODE_FAST / NI_MODE_SCIPY are implemented for the thread-per-trajectory kernels only");
+    const int P = rhs_id == NI_RHS_HEAT1D ? 1 : 2;
+    return compile_stencil_module(std::string("using NiUserStencil = ") + (rhs_id == NI_RHS_HEAT1D ? "NiStencilHeat" : "NiStencilBurgers") + ";\n",
+                                  n, P, method, mode, nullptr, out);
   }
   if (ni_large_builtin(rhs_id, n, method, advanced, &m->large, &m->P, &m->Q)) {
     m->kind = NI_KIND_LARGE;
@@ -344,38 +351,31 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   return NI_OK;
 }
 
-NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
-                                     const char *nvrtc_options, ni_module **out) {
-  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
-  *out = nullptr;
-  if (!stencil_body) return fail(NI_ERR_INVALID, "stencil_body is NULL");
+// NVRTC build of the CTA-per-trajectory kernels for a stencil functor `NiUserStencil` defined by `functor_src`
+static int compile_stencil_module(const std::string &functor_src, int n, int P, int method, int mode,
+                                  const char *nvrtc_options, ni_module **out) {
   if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
   if (P < 0) return fail(NI_ERR_INVALID, "need P >= 0");
+  if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST | NI_MODE_SCIPY)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
   int lg = 0, threads = 0;
   size_t smem = 0;
   if (!ni_large_dims(n, method, &lg, &threads, &smem))
     return fail(NI_ERR_UNSUPPORTED, "stencil systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_N, n);
-  if (mode & ~NI_MODE_ADVANCED) return fail(NI_ERR_UNSUPPORTED, "stencil kernels support NI_MODE_ADVANCED only");
-  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0;
-  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = advanced ? "true" : "false",
-                    C = std::to_string(1 << lg);
-  std::string src;
-  src += "#include \"ni_large.cuh\"\n";
-  src += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P) + ", Q = 0;\n";
-  src += "  NI_DEV static double eval(double t, double ym, double yc, double yp, const double* p, int j, int n) {\n";
-  src += "    (void)t; (void)ym; (void)yc; (void)yp; (void)p; (void)j; (void)n;\n";
-  src += stencil_body;
-  src += "\n  }\n};\n";
+  const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0,
+            scipy = (mode & NI_MODE_SCIPY) ? 1 : 0;
+  const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = scipy ? "2" : advanced ? "1" : "0",
+                    F = fast ? "true" : "false", C = std::to_string(1 << lg);
+  std::string src = "#include \"ni_large.cuh\"\n" + functor_src;
   const std::string lb = "extern \"C\" __global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ";
   src += lb + "ni_user_init(const NiArgs a) { extern __shared__ double s[]; ni_large_init_body<NiUserStencil, " + M +
          ", " + C + ">(a, s); }\n";
   src += lb + "ni_user_run(const NiArgs a) { extern __shared__ double s[]; ni_large_run_body<NiUserStencil, " + M +
-         ", " + A + ", false, " + C + ">(a, s); }\n";
+         ", " + A + ", false, " + C + ", " + F + ">(a, s); }\n";
   src += lb + "ni_user_run_rec(const NiArgs a) { extern __shared__ double s[]; ni_large_run_body<NiUserStencil, " + M +
-         ", " + A + ", true, " + C + ">(a, s); }\n";
+         ", " + A + ", true, " + C + ", " + F + ">(a, s); }\n";
   ni_module *m = new ni_module;
   const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
-  const std::string all_opts = std::string("--fmad=false ") + (nvrtc_options ? nvrtc_options : "");
+  const std::string all_opts = std::string(fast ? "--fmad=true " : "--fmad=false ") + (nvrtc_options ? nvrtc_options : "");
   if (int rc = compile_and_load(src, all_opts.c_str(), names, m)) {
     delete m;
     return rc;
@@ -386,6 +386,8 @@ NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int
   m->Q = 0;
   m->method = method;
   m->advanced = advanced;
+  m->fast = fast;
+  m->scipy = scipy;
   m->S = method == NI_RK45 ? 6 : 3;
   m->block = threads;
   m->smem = smem;
@@ -397,6 +399,21 @@ NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int
   m->large.k_run[1] = m->k_run[1];
   *out = m;
   return NI_OK;
+}
+
+NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
+                                     const char *nvrtc_options, ni_module **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!stencil_body) return fail(NI_ERR_INVALID, "stencil_body is NULL");
+  std::string fsrc;
+  fsrc += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P < 0 ? 0 : P) + ", Q = 0;\n";
+  fsrc += "  template <bool FAST>\n";
+  fsrc += "  NI_DEV static double eval(double t, double ym, double yc, double yp, const double* p, int j, int n) {\n";
+  fsrc += "    (void)t; (void)ym; (void)yc; (void)yp; (void)p; (void)j; (void)n;\n";
+  fsrc += stencil_body;
+  fsrc += "\n  }\n};\n";
+  return compile_stencil_module(fsrc, n, P, method, mode, nvrtc_options, out);
 }
 
 NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages) {

@@ -26,16 +26,20 @@
 // p = (k): dy_j = k (y_{j-1} - 2 y_j + y_{j+1})
 struct NiStencilHeat {
   static constexpr int P = 1, Q = 0;
+  template <bool FAST>
   NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
-    return __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));
+    using A = NiA<FAST>;
+    return A::mul(p[0], A::add(A::nmadd(2.0, yc, ym), yp));  // strict: (ym - 2*yc) + yp
   }
 };
 // p = (nu/dx^2, 1/(2dx)): dy_j = p0 (y_{j-1} - 2 y_j + y_{j+1}) - (y_j p1)(y_{j+1} - y_{j-1})
 struct NiStencilBurgers {
   static constexpr int P = 2, Q = 0;
+  template <bool FAST>
   NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
-    const double diff = __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, yc)), yp));
-    return __dadd_rn(diff, -__dmul_rn(__dmul_rn(yc, p[1]), __dadd_rn(yp, -ym)));
+    using A = NiA<FAST>;
+    const double diff = A::mul(p[0], A::add(A::nmadd(2.0, yc, ym), yp));
+    return A::nmadd(A::mul(yc, p[1]), A::sub(yp, ym), diff);  // diff - (yc*p1)*(yp - ym)
   }
 };
 
@@ -91,7 +95,7 @@ NI_DEV void ni_large_edges(const NiLargeCtx &c, const double (&v)[CPT], int pari
 }
 
 // dy for the CPT components of this thread; components >= n stay exactly zero
-template <class Rhs, int CPT>
+template <class Rhs, int CPT, bool FAST = false>
 NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], const double *p, int parity,
                          double (&out)[CPT]) {
   double left, right;
@@ -100,7 +104,7 @@ NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], 
   for (int i = 0; i < CPT; ++i) {
     const double ym = i == 0 ? left : v[i - 1];
     const double yp = i == CPT - 1 ? right : v[i + 1];
-    out[i] = Rhs::eval(t, ym, v[i], yp, p, c.j0 + i, c.n);
+    out[i] = Rhs::template eval<FAST>(t, ym, v[i], yp, p, c.j0 + i, c.n);
   }
   if (!c.full) {
 #pragma unroll
@@ -161,35 +165,44 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
 #pragma unroll
     for (int i = 0; i < P; ++i) p[i] = a.params_rows[idx * P + i];
     const double t0 = a.t0[idx * a.t0_stride], tb = a.tb0[idx * a.tb_stride];
-    ni_large_rhs<Rhs, CPT>(c, t0, y, p, 0, f0);
+    ni_large_rhs<Rhs, CPT, false>(c, t0, y, p, 0, f0);
     const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
     double h_abs;
     if (a.first_step == 0.0) {
+      // reference: numba fastmath contracts `scale` and `y1` to FMAs; scipy semantics
+      // (a.compat): unfused, h0 capped by the interval, h1 = (0.01 / max(d1, d2)) ** (1 / (order + 1)), result capped
+      // by the interval and max_step
+      const bool sp = a.compat != 0;
+      const double interval = fabs(__dadd_rn(tb, -t0));
       double scale[CPT], tmp[CPT];
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
-        scale[i] = fma(fabs(y[i]), rt[i], at[i]);
+        scale[i] = sp ? __dadd_rn(at[i], __dmul_rn(fabs(y[i]), rt[i])) : fma(fabs(y[i]), rt[i], at[i]);
         tmp[i] = y[i] / scale[i];
       }
       const double d0 = ni_large_rms<CPT>(c, tmp, 0);
 #pragma unroll
       for (int i = 0; i < CPT; ++i) tmp[i] = f0[i] / scale[i];
       const double d1 = ni_large_rms<CPT>(c, tmp, 1);
-      const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : __dmul_rn(0.01, d0) / d1;
+      double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : __dmul_rn(0.01, d0) / d1;
+      if (sp) h0 = fmin(h0, interval);
       const double hd = __dmul_rn(h0, dir);
       double y1[CPT], f1[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) y1[i] = fma(hd, f0[i], y[i]);
-      ni_large_rhs<Rhs, CPT>(c, __dadd_rn(t0, hd), y1, p, 1, f1);
+      for (int i = 0; i < CPT; ++i) y1[i] = sp ? __dadd_rn(y[i], __dmul_rn(hd, f0[i])) : fma(hd, f0[i], y[i]);
+      ni_large_rhs<Rhs, CPT, false>(c, __dadd_rn(t0, hd), y1, p, 1, f1);
 #pragma unroll
       for (int i = 0; i < CPT; ++i) tmp[i] = __dadd_rn(f1[i], -f0[i]) / scale[i];
       const double d2 = ni_large_rms<CPT>(c, tmp, 0) / h0;
       double h1;
       if (d1 <= 1e-15 && d2 <= 1e-15)
         h1 = fmax(1e-6, __dmul_rn(h0, 1e-3));
+      else if (sp)
+        h1 = pow(0.01 / fmax(d1, d2), 1.0 / (NiTab<METHOD>::ORDER + 1));
       else
         h1 = ni_pow_init<NiTab<METHOD>::ORDER + 1>(__dmul_rn(fmax(d1, d2), 100.0));
       h_abs = fmin(__dmul_rn(100.0, h0), h1);
+      if (sp) h_abs = interval == 0.0 ? 0.0 : fmin(h_abs, fmin(interval, a.max_step));
     } else {
       h_abs = fabs(a.first_step);
     }
@@ -219,8 +232,11 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
 }
 
 // ---------------------------------------------------------------- run
-template <class Rhs, int METHOD, bool ADV, bool REC, int CPT>
+// SEM: 0 basic (_step), 1 Advanced (h = h_abs*direction), 2 scipy.integrate semantics; FAST: opt-in fast arithmetic
+// (both as in ni_small_run_body; the AOT library carries SEM 0/1 strict, the other variants are built with NVRTC)
+template <class Rhs, int METHOD, int SEM, bool REC, int CPT, bool FAST = false>
 NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
+  constexpr bool ADV = SEM >= 1, SP = SEM == 2;
   constexpr int P = Rhs::P;
   using Tab = NiTab<METHOD>;
   using Slots = NiLargeSlots<METHOD>;
@@ -262,6 +278,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     int nacc = a.n_acc[idx], nrej = a.n_rej[idx];
     long long att_left = a.max_attempts, acc_left = a.max_accepts;
     bool last_accept = false, fresh = true, done = false;
+    bool srej = SP ? a.step_rejected[idx] != 0 : false;  // scipy: a rejection happened in the current step
     double eps = 0, min_step = 0;
 
     while (!done) {
@@ -273,19 +290,32 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
           break;
         }
         eps = ni_ulp_eps(t, dir);
-        min_step = __dmul_rn(8.0, eps);
-        if (h_abs < min_step) h_abs = min_step;
+        min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);
+        if (SP) {
+          if (!srej) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
+        } else if (h_abs < min_step) {
+          h_abs = min_step;
+        }
         fresh = false;
       }
       // ---- one attempt (_basic.py:145-169)
       const double h_pre = h_abs;
-      if (h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
-      double h = ADV ? __dmul_rn(h_abs, dir) : h_abs;
+      if (SP && h_abs < min_step) {  // scipy tests the step size before every attempt and commits nothing
+        status = NI_ST_FAILED;
+        last_accept = false;
+        break;
+      }
+      if (!SP && h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+      double h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
       double tn = __dadd_rn(t, h);
-      if (__dmul_rn(dir, __dadd_rn(tn, -tb)) >= 0.0) {
-        tn = tb;
-        h = __dadd_rn(tn, -t);
-        h_abs = fabs(h);
+      {
+        const double cross = __dmul_rn(dir, __dadd_rn(tn, -tb));
+        const bool clip = SP ? cross > 0.0 : cross >= 0.0;
+        if (clip) tn = tb;
+        if (clip || SP) {
+          h = __dadd_rn(tn, -t);
+          h_abs = fabs(h);
+        }
       }
       // K_j of component i: register-resident or shared
       auto kget = [&](auto jj, int i) -> double {
@@ -304,9 +334,9 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           const double d = ni_dot_col<METHOD, s, s, false>([&](auto jj) { return kget(jj, i); });
-          ys[i] = __dadd_rn(y[i], __dmul_rn(d, h));
+          ys[i] = NiA<FAST>::madd(d, h, y[i]);
         }
-        ni_large_rhs<Rhs, CPT>(c, __dadd_rn(t, __dmul_rn(ni_cval<METHOD, 0, s>(), h)), ys, p, parity, ks);
+        ni_large_rhs<Rhs, CPT, FAST>(c, NiA<FAST>::madd(ni_cval<METHOD, 0, s>(), h, t), ys, p, parity, ks);
         parity ^= 1;
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
@@ -320,9 +350,9 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
         const double d = ni_dot_col<METHOD, S, S, false>([&](auto jj) { return kget(jj, i); });
-        yn[i] = __dadd_rn(y[i], __dmul_rn(h, d));
+        yn[i] = NiA<FAST>::madd(h, d, y[i]);
       }
-      ni_large_rhs<Rhs, CPT>(c, tn, yn, p, parity, kn);
+      ni_large_rhs<Rhs, CPT, FAST>(c, tn, yn, p, parity, kn);
       parity ^= 1;
       double sq = 0.0;
 #pragma unroll
@@ -343,10 +373,17 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
           rt = 0.0;
           at = 1.0;
         }
-        const double e = __dmul_rn(ed, h) / __dadd_rn(at, __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), rt));
-        sq = __dadd_rn(sq, __dmul_rn(e, e));
+        if constexpr (FAST) {
+          const double e = __dmul_rn(ed, __dmul_rn(h, ni_rcp_fast(fma(fmax(fabs(y[i]), fabs(yn[i])), rt, at))));
+          sq = fma(e, e, sq);
+        } else {
+          const double e = __dmul_rn(ed, h) / __dadd_rn(at, __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), rt));
+          sq = __dadd_rn(sq, __dmul_rn(e, e));
+        }
       }
-      const double en = sqrt(ni_large_block_sum(c, sq, parity & 1) / (double)n);
+      // strict: the RMS norm; fast: the mean square (the controller then takes its 2K-th root, ni_pow_fast)
+      const double msq = ni_large_block_sum(c, sq, parity & 1) / (double)n;
+      const double en = FAST ? msq : sqrt(msq);
       --att_left;
 
       // ---- controller + commit: uniform across the CTA
@@ -360,10 +397,11 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         slot = c.bcast[1];
         park = slot >= a.rec_cap;
       }
-      const double sp = __dmul_rn(0.9, ni_pow_ctrl<Tab::ORDER + 1>(en));
-      const double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
+      double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
-      const bool fail = !ok && !nan && h_new < min_step;
+      const bool fail = !SP && !ok && !nan && h_new < min_step;
       const bool take = (ok && !park) || fail;
       h_abs = park ? h_pre : (nan ? h_abs : h_new);
       if (take) {
@@ -372,10 +410,11 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         for (int i = 0; i < CPT; ++i) y[i] = yn[i];
       }
       if (take || nan) step_h = h;
-      if (!park) {
+      if (!park && !(SP && !ok)) {  // scipy keeps f(t, y) of the accepted point on a rejection
 #pragma unroll
         for (int i = 0; i < CPT; ++i) k0[i] = kn[i];  // K[0] = K[-1] of the next attempt (stale after a reject)
       }
+      if (!park) srej = !ok;
       const bool accepted = ok && !park;
       if (accepted) {
         ++nacc;
@@ -401,7 +440,9 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       last_accept = accepted;
       if (fail) status = NI_ST_FAILED;
       if (nan) status = NI_ST_NONFINITE;
-      done = park || fail || nan || att_left <= 0 || (accepted && acc_left <= 0);
+      done = park || fail || nan;  // (separate statements: see the nvcc note in ni_small_run_body)
+      if (att_left <= 0) done = true;
+      if (accepted && acc_left <= 0) done = true;
       if (accepted && !done && __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
         step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);  // terminal step() of `while step(): pass`
         status = NI_ST_FINISHED;
@@ -426,6 +467,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       a.n_acc[idx] = nacc;
       a.n_rej[idx] = nrej;
       a.running[idx] = last_accept ? 1 : 0;
+      if (SP) a.step_rejected[idx] = srej ? 1 : 0;
       if (status == NI_ST_RUNNING) atomicAdd(a.queue + 2, 1ull);
       if (last_accept) atomicAdd(a.queue + 3, 1ull);
     }
@@ -437,9 +479,9 @@ __global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ni_k_large_init(const
   extern __shared__ double ni_smem[];
   ni_large_init_body<Rhs, METHOD, CPT>(a, ni_smem);
 }
-template <class Rhs, int METHOD, bool ADV, bool REC, int CPT>
+template <class Rhs, int METHOD, int SEM, bool REC, int CPT>
 __global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ni_k_large_run(const NiArgs a) {
   extern __shared__ double ni_smem[];
-  ni_large_run_body<Rhs, METHOD, ADV, REC, CPT>(a, ni_smem);
+  ni_large_run_body<Rhs, METHOD, SEM, REC, CPT, false>(a, ni_smem);
 }
 #endif  // NI_LARGE_CUH

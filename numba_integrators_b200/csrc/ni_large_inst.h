@@ -16,9 +16,9 @@
         RHS::P,                                                                                      \
         RHS::Q,                                                                                      \
         {NI_L_INIT(RHS, NI_RK23), NI_L_INIT(RHS, NI_RK45)},                                          \
-        {{{NI_L_RUN(RHS, NI_RK23, false, false), NI_L_RUN(RHS, NI_RK23, false, true)},               \
-          {NI_L_RUN(RHS, NI_RK23, true, false), NI_L_RUN(RHS, NI_RK23, true, true)}},                \
-         {{NI_L_RUN(RHS, NI_RK45, false, false), NI_L_RUN(RHS, NI_RK45, false, true)},               \
-          {NI_L_RUN(RHS, NI_RK45, true, false), NI_L_RUN(RHS, NI_RK45, true, true)}}}};              \
+        {{{NI_L_RUN(RHS, NI_RK23, 0, false), NI_L_RUN(RHS, NI_RK23, 0, true)},               \
+          {NI_L_RUN(RHS, NI_RK23, 1, false), NI_L_RUN(RHS, NI_RK23, 1, true)}},                \
+         {{NI_L_RUN(RHS, NI_RK45, 0, false), NI_L_RUN(RHS, NI_RK45, 0, true)},               \
+          {NI_L_RUN(RHS, NI_RK45, 1, false), NI_L_RUN(RHS, NI_RK45, 1, true)}}}};              \
     return &k;                                                                                       \
   }

@@ -60,7 +60,10 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.ni_module_builtin(1, 3, 1, 3, m) == 0  # + NI_MODE_FAST
     assert L.ni_module_info(m, *vals) == 0 and vals[4].value == 3
     assert L.ni_module_destroy(m) == 0
-    assert L.ni_module_builtin(3, 64, 1, 2, m) == _lib.NI_ERR_UNSUPPORTED  # no fast mode for the stencil kernels
+    # the opt-in variants of the stencil kernels are specialised with NVRTC: without a GPU that ends in NI_ERR_CUDA
+    # (or NI_ERR_NVRTC where libnvrtc is absent), never in a silent fallback
+    assert L.ni_module_builtin(3, 64, 1, 2, m) in (0, _lib.NI_ERR_CUDA, _lib.NI_ERR_NVRTC)
+    L.ni_module_destroy(m)
     assert L.ni_module_builtin(1, 3, 1, 8, m) == _lib.NI_ERR_INVALID
     assert L.ni_module_destroy(m) == 0
 

@@ -74,3 +74,32 @@ def test_scipy_semantics_too_small_step_commits_nothing():
         pass
     assert s.status == 2 and s.n_accepted == k
     assert abs(s.t - ref.t) <= 1e-9 and s.t < 2.0
+
+
+def test_scipy_semantics_and_fast_arithmetic_on_the_stencil_kernels():
+    """The CTA-per-trajectory kernels get their opt-in variants through NVRTC: heat equation, n = 200."""
+    n, k = 200, 0.8
+    rng = np.random.default_rng(4)
+    x = (np.arange(n) + 1.0) / (n + 1.0)
+    y0 = np.sin(np.pi * x) + 0.05 * rng.standard_normal(n)
+
+    def heat(t, y):
+        ym = np.concatenate(([0.0], y[:-1]))
+        yp = np.concatenate((y[1:], [0.0]))
+        return k * ((ym - 2.0 * y) + yp)
+
+    ref = scipy.integrate.RK45(heat, 0.0, y0, 6.0, rtol=1e-7, atol=1e-9)
+    ours = ni.RK45(ni.rhs.heat1d(k), 0.0, y0, 6.0, rtol=1e-7, atol=1e-9, semantics='scipy')
+    steps = 0
+    while ref.status == 'running':
+        ref.step()
+        assert ni.step(ours)
+        steps += 1
+        assert abs(ours.t - ref.t) <= 1e-9 * max(1.0, ref.t)
+    assert ours.t == 6.0 and ours.n_accepted == steps and not ni.step(ours)
+    assert np.max(np.abs(ours.y - ref.y)) < 1e-10
+    strict = ni.RK45(ni.rhs.heat1d(k), 0.0, y0, 3.0, rtol=1e-8, atol=1e-8)
+    fast = ni.RK45(ni.rhs.heat1d(k), 0.0, y0, 3.0, rtol=1e-8, atol=1e-8, arithmetic='fast')
+    strict.run(), fast.run()
+    assert fast.n_accepted == strict.n_accepted and fast.n_rejected == strict.n_rejected
+    assert np.max(np.abs(fast.y - strict.y)) <= 1e-12 * np.max(np.abs(strict.y))
