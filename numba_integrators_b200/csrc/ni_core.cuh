@@ -339,16 +339,14 @@ NI_DEV double ni_pow_init(double x) {
   return pow(x, -1.0 / K);
 }
 
-// |nextafter(t, dir*inf) - t|  (_basic.py:139), for finite t
+// |nextafter(t, dir*inf) - t|  (_basic.py:139), for finite t.  Integer sign tests instead of FP64 compares: this
+// runs once per attempt in the branch-free hot loop.
 NI_DEV double ni_ulp_eps(double t, double dir) {
-  double nx;
-  if (t == 0.0) {
-    nx = __longlong_as_double(dir > 0.0 ? 1LL : (long long)0x8000000000000001ULL);
-  } else {
-    const long long b = __double_as_longlong(t);
-    nx = __longlong_as_double(((t > 0.0) == (dir > 0.0)) ? b + 1 : b - 1);
-  }
-  return fabs(__dadd_rn(nx, -t));
+  const long long b = __double_as_longlong(t), d = __double_as_longlong(dir);
+  const bool away = (b ^ d) >= 0;          // same sign bit: the neighbour towards dir*inf is further from zero
+  long long nb = away ? b + 1 : b - 1;
+  if ((b << 1) == 0) nb = (d & (long long)0x8000000000000000ULL) | 1LL;  // t == +-0: the smallest denormal
+  return fabs(__dadd_rn(__longlong_as_double(nb), -t));
 }
 
 // ---------------------------------------------------------------- predicates (ff2cond)
@@ -698,7 +696,9 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       const bool upd = act && !park;  // this attempt counts
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
       const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
-      double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
+      // accepted: min(MAX_FACTOR, sp) (en == 0 saturates ni_pow_ctrl, i.e. MAX_FACTOR, :172); rejected:
+      // max(MIN_FACTOR, sp); sp > 0, so one clamp chain with selected bounds serves both
+      double fac = fmin(ok ? 10.0 : __longlong_as_double(0x7ff0000000000000LL), fmax(ok ? 0.0 : 0.2, sp));
       if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
       const bool fail = upd && !SP && !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
