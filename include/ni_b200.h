@@ -116,6 +116,11 @@ int ni_module_compile(const char *rhs_body, int n, int P, int Q, int method, int
  * returning dy_j from y_{j-1}, y_j, y_{j+1} (zero outside 0..n-1); fused into the CTA-per-trajectory kernels. */
 int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
                               const char *nvrtc_options, ni_module **out);
+/* Large systems (n <= 4096) with arbitrary (dense) coupling, written component-wise: `component_body` is the body of
+ *   __device__ double rhs_j(double t, const double* y, int j, int n, const double* p)
+ * returning dy_j; y is the whole stage vector, staged in shared memory by the CTA that owns the trajectory. */
+int ni_module_compile_component(const char *component_body, int n, int P, int method, int mode,
+                                const char *nvrtc_options, ni_module **out);
 int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *mode, int *n_stages);
 /* device layout of the y / klast / aux / params buffers behind ni_ensemble_device_ptr:
  * 0 = component-major [n][N] (thread-per-trajectory kernels), 1 = trajectory-major [N][n] (CTA-per-trajectory) */

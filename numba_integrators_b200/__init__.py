@@ -12,13 +12,13 @@ __version__ = '0.1.0'
 from . import _rhs as rhs
 from . import sr
 from ._lib import NiError
-from ._rhs import BuiltinRHS, CudaRHS, CudaStencilRHS, PythonRHS
+from ._rhs import BuiltinRHS, CudaComponentRHS, CudaRHS, CudaStencilRHS, PythonRHS
 from ._translate import TranslationError, translate, translate_condition
 from ._solver import (ALL, MAX_FACTOR, MIN_FACTOR, RK, RK23, RK45, SAFETY, Advanced, Condition, CudaCondition, Ensemble,
                       Records,
                       Solver, Solvers, StepMask, aux_above, aux_below, convert, ff2cond, ff2t, step, y_above,
                       y_below)
 
-__all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaCondition', 'translate_condition', 'CudaRHS', 'CudaStencilRHS', 'PythonRHS', 'TranslationError', 'translate', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
+__all__ = ['ALL', 'Advanced', 'BuiltinRHS', 'Condition', 'CudaCondition', 'translate_condition', 'CudaComponentRHS', 'CudaRHS', 'CudaStencilRHS', 'PythonRHS', 'TranslationError', 'translate', 'Ensemble', 'NiError', 'RK', 'RK23', 'RK45',
            'Records', 'Solver', 'Solvers', 'StepMask', 'aux_above', 'aux_below', 'convert', 'ff2cond', 'ff2t', 'rhs', 'sr',
            'step', 'y_above', 'y_below', 'SAFETY', 'MIN_FACTOR', 'MAX_FACTOR']

@@ -34,6 +34,7 @@ SIGNATURES = {
     'ni_module_compile': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
                                     C.POINTER(_vp)]),
     'ni_module_compile_stencil': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    'ni_module_compile_component': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)]),
     'ni_module_info': (C.c_int, [_vp] + [C.POINTER(C.c_int)] * 6),
     'ni_module_layout': (C.c_int, [_vp, C.POINTER(C.c_int)]),
     'ni_module_log': (C.c_char_p, [_vp]),

@@ -125,6 +125,32 @@ class CudaStencilRHS(RHS):
         return f'CudaStencilRHS({self.name!r}, P={self.P})'
 
 
+class CudaComponentRHS(RHS):
+    """User right-hand side of a large system (17 <= n <= 4096 is where it pays) with arbitrary coupling, written
+    component-wise: the body of
+
+        __device__ double rhs_j(double t, const double* y, int j, int n, const double* p)
+
+    returning dy_j.  One CTA integrates one trajectory; `y` is the stage vector in shared memory."""
+    shared_module = True
+
+    def __init__(self, body, P=0, parameters=None, name='user_component', nvrtc_options=''):
+        self.body, self.P, self.Q, self.n, self.name = str(body), int(P), 0, None, name
+        self.nvrtc_options = nvrtc_options
+        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
+
+    def _module(self, n, method, mode):
+        def make():
+            out = _lib._vp()
+            _lib.check(_lib.lib().ni_module_compile_component(self.body.encode(), int(n), self.P, int(method),
+                                                              int(mode), self.nvrtc_options.encode(), out))
+            return out
+        return _cached_module(('component', self.body, int(n), self.P, 0, int(method), int(mode), self.nvrtc_options), make)
+
+    def __repr__(self):
+        return f'CudaComponentRHS({self.name!r}, P={self.P})'
+
+
 harmonic = BuiltinRHS('harmonic')
 sine = harmonic
 lorenz63 = BuiltinRHS('lorenz63')

@@ -99,7 +99,7 @@ static const NiKernelSet *builtin_small(int rhs_id, int n) {
 }
 
 static int compile_stencil_module(const std::string &functor_src, int n, int P, int method, int mode,
-                                  const char *nvrtc_options, ni_module **out);
+                                  const char *nvrtc_options, ni_module **out, bool component = false);
 
 NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
@@ -353,14 +353,14 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
 
 // NVRTC build of the CTA-per-trajectory kernels for a stencil functor `NiUserStencil` defined by `functor_src`
 static int compile_stencil_module(const std::string &functor_src, int n, int P, int method, int mode,
-                                  const char *nvrtc_options, ni_module **out) {
+                                  const char *nvrtc_options, ni_module **out, bool component) {
   if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
   if (P < 0) return fail(NI_ERR_INVALID, "need P >= 0");
   if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST | NI_MODE_SCIPY)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
   int lg = 0, threads = 0;
   size_t smem = 0;
-  if (!ni_large_dims(n, method, &lg, &threads, &smem))
-    return fail(NI_ERR_UNSUPPORTED, "stencil systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_N, n);
+  if (!ni_large_dims(n, method, &lg, &threads, &smem, component))
+    return fail(NI_ERR_UNSUPPORTED, "CTA-per-trajectory systems support 1 <= n <= %d (got %d)", NI_LARGE_MAX_N, n);
   const int advanced = (mode & NI_MODE_ADVANCED) ? 1 : 0, fast = (mode & NI_MODE_FAST) ? 1 : 0,
             scipy = (mode & NI_MODE_SCIPY) ? 1 : 0;
   const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = scipy ? "2" : advanced ? "1" : "0",
@@ -408,12 +408,27 @@ NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int
   if (!stencil_body) return fail(NI_ERR_INVALID, "stencil_body is NULL");
   std::string fsrc;
   fsrc += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P < 0 ? 0 : P) + ", Q = 0;\n";
-  fsrc += "  template <bool FAST>\n";
+  fsrc += "  static constexpr bool COMPONENT = false;\n  template <bool FAST>\n";
   fsrc += "  NI_DEV static double eval(double t, double ym, double yc, double yp, const double* p, int j, int n) {\n";
   fsrc += "    (void)t; (void)ym; (void)yc; (void)yp; (void)p; (void)j; (void)n;\n";
   fsrc += stencil_body;
   fsrc += "\n  }\n};\n";
   return compile_stencil_module(fsrc, n, P, method, mode, nvrtc_options, out);
+}
+
+NI_API int ni_module_compile_component(const char *component_body, int n, int P, int method, int mode,
+                                       const char *nvrtc_options, ni_module **out) {
+  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!component_body) return fail(NI_ERR_INVALID, "component_body is NULL");
+  std::string fsrc;
+  fsrc += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P < 0 ? 0 : P) + ", Q = 0;\n";
+  fsrc += "  static constexpr bool COMPONENT = true;\n  template <bool FAST>\n";
+  fsrc += "  NI_DEV static double eval(double t, const double* y, int j, int n, const double* p) {\n";
+  fsrc += "    (void)t; (void)y; (void)j; (void)n; (void)p;\n";
+  fsrc += component_body;
+  fsrc += "\n  }\n};\n";
+  return compile_stencil_module(fsrc, n, P, method, mode, nvrtc_options, out, true);
 }
 
 NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages) {

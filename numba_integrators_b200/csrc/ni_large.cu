@@ -5,14 +5,14 @@
 #include "ni_host.h"
 #include "ni_rhs_builtin.cuh"
 
-NI_VISIBLE_INTERNAL bool ni_large_dims(int n, int method, int *lg_out, int *threads, size_t *smem_bytes) {
+NI_VISIBLE_INTERNAL bool ni_large_dims(int n, int method, int *lg_out, int *threads, size_t *smem_bytes, bool component) {
   if (n < 1 || n > NI_LARGE_MAX_N) return false;
   int lg = 0;  // components per thread = 1 << lg: the smallest that fits NI_LARGE_MAX_THREADS threads
   while ((n + (1 << lg) - 1) / (1 << lg) > NI_LARGE_MAX_THREADS) ++lg;
   const int cpt = 1 << lg;
   *lg_out = lg;
   *threads = ((n + cpt - 1) / cpt + 31) / 32 * 32;
-  *smem_bytes = ni_large_smem_doubles(method, *threads, cpt) * sizeof(double);
+  *smem_bytes = ni_large_smem_doubles(method, *threads, cpt, component) * sizeof(double);
   return true;
 }
 

@@ -26,6 +26,7 @@
 // p = (k): dy_j = k (y_{j-1} - 2 y_j + y_{j+1})
 struct NiStencilHeat {
   static constexpr int P = 1, Q = 0;
+  static constexpr bool COMPONENT = false;
   template <bool FAST>
   NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
     using A = NiA<FAST>;
@@ -35,6 +36,7 @@ struct NiStencilHeat {
 // p = (nu/dx^2, 1/(2dx)): dy_j = p0 (y_{j-1} - 2 y_j + y_{j+1}) - (y_j p1)(y_{j+1} - y_{j-1})
 struct NiStencilBurgers {
   static constexpr int P = 2, Q = 0;
+  static constexpr bool COMPONENT = false;
   template <bool FAST>
   NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
     using A = NiA<FAST>;
@@ -65,10 +67,11 @@ struct NiLargeSlots {
 
 // dynamic shared memory of one CTA, in doubles.  Stage vectors are laid out [slot][component][NI_LARGE_MAX_THREADS]
 // whatever the CTA size, so that every access is `thread base + immediate offset`.
-NI_HD constexpr size_t ni_large_smem_doubles(int method, int threads, int cpt) {
-  (void)threads;
+// Component right-hand sides (dense coupling) additionally stage the whole stage vector: + threads * cpt doubles.
+NI_HD constexpr size_t ni_large_smem_doubles(int method, int threads, int cpt, bool component = false) {
   return (size_t)(method == NI_RK45 ? NiLargeSlots<NI_RK45>::TOTAL : NiLargeSlots<NI_RK23>::TOTAL) *
-             NI_LARGE_MAX_THREADS * cpt + 4 * (size_t)NI_LARGE_MAX_THREADS + 2 * 32 + 8;
+             NI_LARGE_MAX_THREADS * cpt + 4 * (size_t)NI_LARGE_MAX_THREADS + 2 * 32 + 8 +
+         (component ? (size_t)threads * cpt : 0);
 }
 
 struct NiLargeCtx {
@@ -76,9 +79,20 @@ struct NiLargeCtx {
   double *edge;   // [2 parity][2 sides][T]
   double *part;   // [2 parity][32] per-warp partial sums
   long long *bcast;
+  double *ys;     // component right-hand sides only: the full stage vector [n]
   int T, tid, n, j0;
   bool full;  // n == T * CPT: no padding components, masks are skipped
 };
+
+// Component index of local slot i.  Stencil kernels: CPT contiguous components per thread (neighbours in
+// registers).  Component kernels: strided ownership (tid, tid + T, ...): conflict-free staging of the stage vector.
+template <class Rhs>
+NI_DEV int ni_large_j(const NiLargeCtx &c, int i) {
+  if constexpr (Rhs::COMPONENT)
+    return c.tid + i * c.T;
+  else
+    return c.j0 + i;
+}
 
 // neighbour exchange: returns y_{j0-1} and y_{j0+CPT} of this thread for the stage vector `v`.  Two staging buffers
 // alternate, so one CTA barrier per exchange is enough.  (Measured alternative: per-warp sequence flags +
@@ -98,17 +112,34 @@ NI_DEV void ni_large_edges(const NiLargeCtx &c, const double (&v)[CPT], int pari
 template <class Rhs, int CPT, bool FAST = false>
 NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], const double *p, int parity,
                          double (&out)[CPT]) {
-  double left, right;
-  ni_large_edges<CPT>(c, v, parity, left, right);
+  if constexpr (Rhs::COMPONENT) {
+    // dense coupling: stage the whole vector in shared memory, every thread evaluates its own components from it
+    (void)parity;
+    __syncthreads();  // the previous stage vector is no longer read
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) {
-    const double ym = i == 0 ? left : v[i - 1];
-    const double yp = i == CPT - 1 ? right : v[i + 1];
-    out[i] = Rhs::template eval<FAST>(t, ym, v[i], yp, p, c.j0 + i, c.n);
-  }
-  if (!c.full) {
+    for (int i = 0; i < CPT; ++i) {
+      const int j = c.tid + i * c.T;
+      if (j < c.n) c.ys[j] = v[i];
+    }
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) out[i] = (c.j0 + i < c.n) ? out[i] : 0.0;
+    for (int i = 0; i < CPT; ++i) {
+      const int j = c.tid + i * c.T;
+      out[i] = j < c.n ? Rhs::template eval<FAST>(t, (const double *)c.ys, j, c.n, p) : 0.0;
+    }
+  } else {
+    double left, right;
+    ni_large_edges<CPT>(c, v, parity, left, right);
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const double ym = i == 0 ? left : v[i - 1];
+      const double yp = i == CPT - 1 ? right : v[i + 1];
+      out[i] = Rhs::template eval<FAST>(t, ym, v[i], yp, p, c.j0 + i, c.n);
+    }
+    if (!c.full) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) out[i] = (c.j0 + i < c.n) ? out[i] : 0.0;
+    }
   }
 }
 
@@ -144,6 +175,7 @@ NI_DEV NiLargeCtx ni_large_ctx(const NiArgs &a, double *smem, int cpt, int total
   c.edge = smem + (size_t)total_slots * NI_LARGE_MAX_THREADS * cpt;
   c.part = c.edge + 4 * NI_LARGE_MAX_THREADS;
   c.bcast = (long long *)(c.part + 64);
+  c.ys = (double *)(c.bcast + 8);
   return c;
 }
 
@@ -157,7 +189,7 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
     double y[CPT], f0[CPT], p[P > 0 ? P : 1], rt[CPT], at[CPT];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      const int j = c.j0 + i;
+      const int j = ni_large_j<Rhs>(c, i);
       y[i] = j < n ? a.y0_rows[idx * n + j] : 0.0;
       rt[i] = j < n ? a.rtol_d[j] : 0.0;
       at[i] = j < n ? a.atol_d[j] : 1.0;
@@ -208,7 +240,7 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
     }
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      const int j = c.j0 + i;
+      const int j = ni_large_j<Rhs>(c, i);
       if (j < n) {
         a.y[idx * n + j] = y[i];
         a.klast[idx * n + j] = f0[i];
@@ -268,7 +300,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     double y[CPT], k0[CPT], k2[CPT], p[P > 0 ? P : 1];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      const int j = c.j0 + i;
+      const int j = ni_large_j<Rhs>(c, i);
       y[i] = j < n ? a.y[idx * n + j] : 0.0;
       k0[i] = j < n ? a.klast[idx * n + j] : 0.0;
       k2[i] = 0.0;
@@ -358,7 +390,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
         sv(Slots::slot(S), i) = kn[i];
-        const int j = c.j0 + i;
+        const int j = ni_large_j<Rhs>(c, i);
         const double ed = ni_dot_col<METHOD, S + 1, S + 1, false>([&](auto jj) {
           if constexpr (decltype(jj)::value == S)
             return kn[i];
@@ -422,7 +454,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         if (REC) {
 #pragma unroll
           for (int i = 0; i < CPT; ++i)
-            if (c.j0 + i < n) a.rec_y[slot * n + c.j0 + i] = y[i];
+            if (ni_large_j<Rhs>(c, i) < n) a.rec_y[slot * n + ni_large_j<Rhs>(c, i)] = y[i];
           if (tid == 0) {
             a.rec_traj[slot] = (unsigned int)idx;
             a.rec_step[slot] = (unsigned int)nacc;
@@ -453,7 +485,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     // ---- retire
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-      const int j = c.j0 + i;
+      const int j = ni_large_j<Rhs>(c, i);
       if (j < n) {
         a.y[idx * n + j] = y[i];
         a.klast[idx * n + j] = k0[i];

@@ -21,6 +21,6 @@ const NiLargeKernels *ni_large_kernels_heat();
 const NiLargeKernels *ni_large_kernels_burgers();
 
 // CTA shape for a state dimension n <= 4096: components per thread = 1 << lg, threads, dynamic shared memory.
-bool ni_large_dims(int n, int method, int *lg, int *threads, size_t *smem_bytes);
+bool ni_large_dims(int n, int method, int *lg, int *threads, size_t *smem_bytes, bool component = false);
 // Returns false when (rhs_id, n) has no CTA-per-trajectory kernel.
 bool ni_large_builtin(int rhs_id, int n, int method, int advanced, NiLargePlan *plan, int *P, int *Q);

@@ -443,3 +443,36 @@ def test_module_caches(tmp_path, monkeypatch):
     assert t_warm < t_cold
     a.run(), c.run()
     assert a.y == c.y and abs(a.y[0] - np.exp(-1.2345)) < 1e-3
+
+
+def test_component_rhs_dense_large_system():
+    """ni.CudaComponentRHS: one CTA per trajectory, the whole stage vector staged in shared memory, arbitrary coupling.
+    (a) a mean-field Kuramoto model with n = 300 oscillators against SciPy; (b) the heat equation written
+    component-wise against the stencil kernel (same arithmetic per component, different reduction order)."""
+    import scipy.integrate
+    n = 300
+    body = '''
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += sin(y[k] - y[j]);
+        return p[0] + 0.002 * j + p[1] / n * s;
+    '''
+    rng = np.random.default_rng(12)
+    y0 = rng.uniform(-np.pi, np.pi, size=(5, n))
+    par = np.column_stack([rng.uniform(0.5, 1.0, 5), rng.uniform(0.5, 2.0, 5)])
+    ens = ni.RK45(ni.CudaComponentRHS(body, P=2), 0.0, y0, 2.0, rtol=1e-9, atol=1e-11, parameters=par)
+    assert ens.run() == 0 and np.all(ens.t == 2.0) and np.all(ens.status == 1)
+
+    def kuramoto(t, y, w, K):
+        return w + 0.002 * np.arange(n) + K / n * np.sin(y[None, :] - y[:, None]).sum(axis=1)
+    for i in (0, 4):
+        ref = scipy.integrate.solve_ivp(kuramoto, (0, 2.0), y0[i], args=tuple(par[i]), rtol=1e-11, atol=1e-13)
+        assert np.max(np.abs(ens.y[i] - ref.y[:, -1])) < 1e-7
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c5_heat(N=4, n=777, t_bound=3.0)
+    comp = ni.CudaComponentRHS('const double ym = j > 0 ? y[j - 1] : 0.0, yp = j + 1 < n ? y[j + 1] : 0.0;'
+                               'return __dmul_rn(p[0], __dadd_rn(__dadd_rn(ym, -__dmul_rn(2.0, y[j])), yp));', P=1)
+    a = ni.RK45(comp, 0.0, w.y0, 3.0, rtol=1e-8, atol=1e-8, parameters=w.params)
+    b = ni.RK45(ni.rhs.heat1d(w.params[:, 0]), 0.0, w.y0, 3.0, rtol=1e-8, atol=1e-8)
+    a.run(), b.run()
+    assert np.array_equal(a.n_accepted, b.n_accepted) and np.array_equal(a.n_rejected, b.n_rejected)
+    assert np.max(np.abs(a.y - b.y)) <= 1e-12 * np.max(np.abs(b.y))
