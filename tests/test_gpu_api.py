@@ -182,11 +182,16 @@ def test_device_views_and_nccl_gather_single_rank():
     assert np.array_equal(tens['y'].t().cpu().numpy(), ens.y)
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29533')
+    h = wl.c5_heat(N=6, n=300, t_bound=1.0)                      # trajectory-major device layout
+    big = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 1.0, rtol=1e-8, atol=1e-8)
+    big.run()
     dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))
     try:
         full = nd.gather(ens)
+        full_big = nd.gather(big)
     finally:
         dist.destroy_process_group()
+    assert np.array_equal(full_big['y'], big.y) and np.array_equal(full_big['n_accepted'], big.n_accepted)
     assert np.array_equal(full['y'], ens.y) and np.array_equal(full['t'], ens.t)
     assert np.array_equal(full['auxiliary'], ens.auxiliary) and np.array_equal(full['n_accepted'], ens.n_accepted)
 
