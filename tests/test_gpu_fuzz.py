@@ -1,6 +1,8 @@
 """Randomised differential test: GPU (through the facade / C ABI) against the CPU oracle over random
 configurations -- method, right-hand side, tolerances (scalar and per-component), horizon, direction, max_step,
 first_step, per-trajectory t0 / t_bound, ensemble size (ragged), lock-step vs fast-forward vs ff2t legs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -55,7 +57,7 @@ def build(cfg):
     return ctor(f, cfg['t0'], cfg['y0'], cfg['t_bound'], **kw)
 
 
-@pytest.mark.parametrize('seed', range(60))
+@pytest.mark.parametrize('seed', range(int(os.environ.get('NI_FUZZ_SEEDS', '60'))))
 def test_random_configuration_matches_oracle(seed, oracle):
     cfg = make_case(seed)
     s = build(cfg)
