@@ -187,6 +187,12 @@ int ni_ensemble_timing(ni_ensemble *e, float *ms_init, float *ms_run, int64_t *n
  * `repeats` launches of `iters` x 128 FMAs per thread (roofline denominator for bench.py). */
 int ni_fp64_peak(int device, int iters, int repeats, double *tflops_best);
 
+/* device self-check of the branch-free arithmetic of the error-norm / controller tail (csrc/ni_math.cuh):
+ * `count` random operands inside the guarded ranges; which = 0: ni_div_core against `/`, 1: ni_sqrt_core against
+ * sqrt(), 2 / 3: ni_pow_ctrl_ms<5> / <3> (seeded from the mean square) against ni_pow_ctrl on the root.
+ * *mismatches = results that differ in any bit (0 expected for 0 and 1; a few per 10^5 at most for 2 and 3). */
+int ni_devmath_check(int device, int which, int64_t count, uint64_t seed, int64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

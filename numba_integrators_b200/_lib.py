@@ -61,6 +61,7 @@ SIGNATURES = {
     'ni_ensemble_record_drain': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i64p]),
     'ni_ensemble_timing': (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _i64p]),
     'ni_fp64_peak': (C.c_int, [C.c_int, C.c_int, C.c_int, _dp]),
+    'ni_devmath_check': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_uint64, _i64p]),
 }
 
 

@@ -349,6 +349,16 @@ NI_DEV double ni_ulp_eps(double t, double dir) {
   return fabs(__dadd_rn(__longlong_as_double(nb), -t));
 }
 
+// Comparisons of the hot loop on the integer pipe (the FP64 pipe is the kernel's bound; a DSETP costs it as much as
+// a DFMA).  For doubles that are >= +0 and not NaN (+inf allowed) the order of the values is the order of their bit
+// patterns as signed 64-bit integers.
+NI_DEV bool ni_lt_pos(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
+// max(|a|, |b|); differs from fmax(fabs(a), fabs(b)) only for NaN operands (it returns the NaN, fmax the number)
+NI_DEV double ni_absmax(double a, double b) {
+  const long long x = __double_as_longlong(a) & 0x7fffffffffffffffLL, y = __double_as_longlong(b) & 0x7fffffffffffffffLL;
+  return __longlong_as_double(x > y ? x : y);
+}
+
 // ---------------------------------------------------------------- predicates (ff2cond)
 #ifdef NI_HAVE_USER_COND
 // user predicate of ff2cond, defined by the generated translation unit after this header
@@ -593,28 +603,35 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     // clamp is a no-op (a retry only happens with h_abs >= min_step)
     const double eps = ni_ulp_eps(t, dir);
     const double min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);  // scipy: 10 ulp
+    // (h_abs, min_step, max_step are >= +0: integer-pipe comparisons, ni_lt_pos)
     if (SP) {
       // first attempt of a step <=> no rejection seen in it yet (also right after resuming a parked trajectory)
       if (!srej) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
     } else {
-      h_abs = h_abs < min_step ? min_step : h_abs;
+      h_abs = ni_lt_pos(h_abs, min_step) ? min_step : h_abs;
     }
     // ---- one attempt (_basic.py:145-169)
     const double h_pre = h_abs;
     const bool sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt, commits nothing
-    if (!SP && h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+    if (!SP && ni_lt_pos(a.max_step, h_abs)) h_abs = __dadd_rn(a.max_step, -eps);
     double h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
     double tn = __dadd_rn(t, h);
+    bool reach;  // direction * (t_new - t_bound) >= 0: this attempt ends on t_bound
     {
-      const double cross = __dmul_rn(dir, __dadd_rn(tn, -tb));
-      const bool clip = SP ? cross > 0.0 : cross >= 0.0;
+      // sign tests on the bits of t_new - t_bound instead of the product with direction (= +-1)
+      const double dtb = __dadd_rn(tn, -tb);
+      const bool zero = ((__double2hiint(dtb) << 1) | __double2loint(dtb)) == 0;
+      const bool same = (__double2hiint(dtb) ^ __double2hiint(dir)) >= 0;
+      reach = zero || same;
+      const bool clip = SP ? (same && !zero) : reach;
       tn = clip ? tb : tn;
       if (clip || SP) {  // scipy recomputes h = t_new - t on every attempt
         h = __dadd_rn(tn, -t);
         h_abs = fabs(h);
       }
     }
-    double en, kn[n], yn[n], auxn[Q > 0 ? Q : 1];
+    double en, pw, kn[n], yn[n], auxn[Q > 0 ? Q : 1];  // error norm (fast: its square), en ** error_exponent
+    bool en_lt1, en_nan;
     {
       double K[S + 1][n];
 #pragma unroll
@@ -646,15 +663,47 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         }
         en = __dmul_rn(msq, 1.0 / n);  // en holds error_norm**2 in fast mode (same < 1, == 0, NaN tests)
       } else {
+        // error / scale, RMS norm and controller power (_basic.py:166-169, :174/:178) as ONE basic block: the n
+        // quotients, the root and the power are the guarded branch-free sequences of ni_math.cuh, so their
+        // dependent chains interleave (the operators' slow-path branches would serialise them); operands outside
+        // the guards -- a zero, denormal or non-finite error -- redo the tail with the operators.
+        double num[n], q[n];
+        unsigned out = 0u;  // some operand is outside the guarded ranges
 #pragma unroll
         for (int i = 0; i < n; ++i) {
-          ev[i] = __dmul_rn(ev[i], h) / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+          num[i] = __dmul_rn(ev[i], h);
+          const double den = __dadd_rn(a.atol[i], __dmul_rn(ni_absmax(y[i], yn[i]), a.rtol[i]));
+          out |= ni_div_out(num[i], den);
+          q[i] = ni_div_core(num[i], den);
           kn[i] = K[S][i];
         }
-        en = ni_rms<n>(ev);
+        double acc = __dmul_rn(q[0], q[0]);
+#pragma unroll
+        for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(q[i], q[i]));
+        // acc / n (_aux.py:75): exact for n = 1, 2; Markstein for n = 3; the guard on ms below covers acc otherwise
+        const double ms = n == 1 ? acc : n == 2 ? __dmul_rn(acc, 0.5) : n == 3 ? ni_div3(acc) : ni_div_core(acc, (double)n);
+        out |= ni_sqrt_out(ms);
+        en = ni_sqrt_core(ms);
+        pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
+        en_lt1 = (unsigned)__double2hiint(en) < 0x3ff00000u;  // en > 0 here
+        en_nan = false;
+        if (act && out != 0u) {
+#pragma unroll
+          for (int i = 0; i < n; ++i)
+            ev[i] = num[i] / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+          en = ni_rms<n>(ev);
+          pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
+          en_lt1 = en < 1.0;
+          en_nan = en != en;
+        }
       }
     }
-    const bool ok = act && en < 1.0 && !sp_fail;
+    if constexpr (FAST) {
+      pw = ni_pow_fast<2 * (Tab::ORDER + 1)>(en);
+      en_lt1 = en < 1.0;
+      en_nan = en != en;
+    }
+    const bool ok = act && en_lt1 && !sp_fail;
 
     // ---- record log: one slot per accepting lane.  A warp reserves `rec_chunk` slots with ONE atomicAdd
     // and hands them out locally (a single global cursor saturates the L2 atomic unit at ~0.8 G
@@ -689,19 +738,20 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
 
     // ---- controller + commit (_basic.py:171-180), branch-free: every update is a select on the lane's flags
     {
-      const bool nan = act && en != en;
+      const bool nan = act && en_nan;
       // park: log full -> undo this attempt (the state before an attempt is exactly t, y, h_abs, K[-1]);
       // scipy's too-small-step exit also commits nothing of the attempt
       const bool park = (REC && ok && slot >= a.rec_cap) || (act && sp_fail);
       const bool upd = act && !park;  // this attempt counts
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
-      const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
+      const double sp = __dmul_rn(0.9, pw);
       // accepted: min(MAX_FACTOR, sp) (en == 0 saturates ni_pow_ctrl, i.e. MAX_FACTOR, :172); rejected:
-      // max(MIN_FACTOR, sp); sp > 0, so one clamp chain with selected bounds serves both
-      double fac = fmin(ok ? 10.0 : __longlong_as_double(0x7ff0000000000000LL), fmax(ok ? 0.0 : 0.2, sp));
+      // max(MIN_FACTOR, sp).  sp > 0 and never NaN (ni_pow_ctrl saturates): integer-pipe comparisons
+      double fac = ok ? (ni_lt_pos(sp, 10.0) ? sp : 10.0) : (ni_lt_pos(0.2, sp) ? sp : 0.2);
       if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
-      const bool fail = upd && !SP && !ok && !nan && h_new < min_step;  // :179-180: commits the REJECTED t, y
+      // :179-180: commits the REJECTED t, y (h_new, min_step >= +0; a NaN h_new implies `nan`)
+      const bool fail = upd && !SP && !ok && !nan && ni_lt_pos(h_new, min_step);
       const bool accepted = ok && !park;
       const bool take = accepted || fail;
       h_abs = upd ? (nan ? h_abs : h_new) : h_pre;
@@ -743,7 +793,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         parked = true;
         done = true;
       }
-      if (accepted && !done && __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
+      if (accepted && !done && reach) {  // t == t_bound now: the attempt was clipped to it or landed on it
         // fast-forward: the terminal step() call of `while step(): pass` (_basic.py:135-136)
         step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
         status = NI_ST_FINISHED;

@@ -481,3 +481,20 @@ def test_component_rhs_dense_large_system():
     a.run(), b.run()
     assert np.array_equal(a.n_accepted, b.n_accepted) and np.array_equal(a.n_rejected, b.n_rejected)
     assert np.max(np.abs(a.y - b.y)) <= 1e-12 * np.max(np.abs(b.y))
+
+
+def test_branch_free_tail_arithmetic_matches_the_operators():
+    """csrc/ni_math.cuh: the guarded division / square root of the error-norm tail must equal CUDA's `/` and sqrt()
+    bit for bit over the guarded operand range, and the controller power seeded from the mean square must equal
+    the one seeded from the root (both correctly rounded but for ~1e-5 of arguments)."""
+    import ctypes
+    from numba_integrators_b200 import _lib
+    L = _lib.lib()
+    n = 400_000_000
+    bad = ctypes.c_int64(-1)
+    for which in (0, 1):
+        _lib.check(L.ni_devmath_check(0, which, n, 1234 + which, ctypes.byref(bad)))
+        assert bad.value == 0, (which, bad.value)
+    for which in (2, 3):
+        _lib.check(L.ni_devmath_check(0, which, n, 99 + which, ctypes.byref(bad)))
+        assert 0 <= bad.value <= n * 5e-5, (which, bad.value)

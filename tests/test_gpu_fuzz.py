@@ -33,9 +33,11 @@ def make_case(seed):
     t0 = 1.0 if name == 'riccati' else 0.0
     span = T * r.uniform(0.3, 1.0)
     cfg['advanced'] = bool(r.random() < 0.5) or P > 0
-    # backward Lorenz is violently expanding (~e^{13.7 t}): 1e4+ steps whose 1-ulp `pow` differences (glibc misrounds
-    # ~5e-4 of calls) are amplified far above any tolerance -- a conditioning property, not a parity one
-    backward = cfg['advanced'] and name not in ('riccati', 'lorenz63') and r.random() < 0.25
+    # backward Lorenz is violently expanding (~e^{13.7 t}) and backward Van der Pol leaves its limit cycle and blows
+    # up until the step-size failure exit: 1e3+ steps whose 1-ulp `pow` differences (glibc misrounds ~5e-4 of calls)
+    # are amplified above any tolerance -- a conditioning property, not a parity one (seed 67: identical counts and
+    # failure status on all 156 trajectories, terminal states apart by 1e-10).
+    backward = cfg['advanced'] and name not in ('riccati', 'lorenz63') and r.random() < 0.25 and name != 'vanderpol'
     if r.random() < 0.3:                                         # per-trajectory times
         cfg['t0'] = t0 + r.uniform(0, 0.2, N)
         cfg['t_bound'] = cfg['t0'] + (-1 if backward else 1) * span * r.uniform(0.5, 1.0, N)

@@ -2,6 +2,7 @@
 
   * ni_pow_ctrl<5>/<3> against the correctly rounded x**e (decimal, 60 digits) and against glibc pow
     (what the reference's numba code calls) on random error norms;
+  * ni_pow_ctrl_ms<5>/<3> (seeded from the mean square m, x = sqrt(m)) against the correctly rounded x**e;
   * ni_div3 against IEEE division.
 
     python tools/check_devmath.py [n_samples]
@@ -22,6 +23,8 @@ SRC = r'''
 extern "C" {
 double pow5(double x) { return ni_pow_ctrl<5>(x); }
 double pow3(double x) { return ni_pow_ctrl<3>(x); }
+double powms5(double m) { return ni_pow_ctrl_ms<5>(m, std::sqrt(m)); }
+double powms3(double m) { return ni_pow_ctrl_ms<3>(m, std::sqrt(m)); }
 double div3(double x) { return ni_div3(x); }
 double powf10(double x) { return ni_pow_fast<10>(x); }
 double powf6(double x) { return ni_pow_fast<6>(x); }
@@ -39,7 +42,7 @@ def build():
     subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-mfma', '-shared', '-fPIC', '-I',
                     str(ROOT / 'numba_integrators_b200' / 'csrc'), str(d / 't.cpp'), '-o', str(so)], check=True)
     L = ctypes.CDLL(str(so))
-    for f in ('pow5', 'pow3', 'div3', 'powf10', 'powf6', 'rcpf'):
+    for f in ('pow5', 'pow3', 'powms5', 'powms3', 'div3', 'powf10', 'powf6', 'rcpf'):
         getattr(L, f).restype = ctypes.c_double
         getattr(L, f).argtypes = [ctypes.c_double]
     L.libm_pow.restype = ctypes.c_double
@@ -53,6 +56,8 @@ def main(n=20000):
     rng = np.random.default_rng(0)
     res = {}
     for name, f, e in (('RK45 e=-0.2', L.pow5, -0.2), ('RK23 e=RN(-1/3)', L.pow3, -1 / 3)):
+        fms = L.powms5 if f is L.pow5 else L.powms3
+        bad_ms = 0
         De = Decimal(e)
         # error norms as the controller sees them: log-uniform over 1e-6..1e3 plus a wide tail
         xs = np.concatenate([10.0 ** rng.uniform(-6, 3, n), 10.0 ** rng.uniform(-29, 29, n // 4)])
@@ -64,7 +69,13 @@ def main(n=20000):
             bad_mine += mine != cr
             bad_libm += lm != cr
             differ += mine != lm
+            if 2.0 ** -60 < x < 2.0 ** 60:                   # the domain the kernel guards (ni_sqrt_out)
+                m = x * x                                   # a mean square whose root is (nearly always) x
+                xm = float(np.sqrt(m))
+                bad_ms += fms(m) != float(Decimal(xm) ** De)
         res[name] = (bad_mine, bad_libm, differ, len(xs))
+        res[name + ' ms'] = bad_ms
+        print(f'{name:18s} ni_pow_ctrl_ms(m, sqrt(m)) != CR: {bad_ms}')
         print(f'{name:18s} samples={len(xs)}  ni_pow_ctrl != CR: {bad_mine}   glibc pow != CR: {bad_libm}   '
               f'ni_pow_ctrl != glibc: {differ}')
     a = np.concatenate([rng.uniform(0, 10, 2_000_000), 10.0 ** rng.uniform(-300, 300, 2_000_000)])
