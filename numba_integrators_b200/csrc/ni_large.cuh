@@ -54,7 +54,7 @@ template <int METHOD, int J>
 struct NiKInReg {
   static constexpr bool value = (J == 0) || (NI_LARGE_K2_IN_REG && METHOD == NI_RK45 && J == 2);
 };
-// shared-memory slot of stage vector J (1..S; J = S is the new FSAL stage) and the slot count
+// shared-memory slot of stage vector J (1..S-1; the new FSAL stage K_S never leaves registers) and the slot count
 template <int METHOD>
 struct NiLargeSlots {
   NI_HD static constexpr int slot(int j) {
@@ -62,7 +62,7 @@ struct NiLargeSlots {
     for (int k = 1; k < j; ++k) s += (NI_LARGE_K2_IN_REG && METHOD == NI_RK45 && k == 2) ? 0 : 1;
     return s;
   }
-  static constexpr int KSLOTS = slot(NiTab<METHOD>::S) + 1, TOTAL = KSLOTS;
+  static constexpr int KSLOTS = slot(NiTab<METHOD>::S), TOTAL = KSLOTS > 0 ? KSLOTS : 1;
 };
 
 // dynamic shared memory of one CTA, in doubles.  Stage vectors are laid out [slot][component][NI_LARGE_MAX_THREADS]
@@ -143,17 +143,26 @@ NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], 
   }
 }
 
-// sum over the block of `x` (fixed order: lanes by butterfly, then warps sequentially); all threads get it
+// sum over the block of `x`; all threads get it.  Fixed order: lanes by butterfly, then the per-warp partials by a
+// pairwise tree over all NI_LARGE_MAX_THREADS / 32 slots (slots of absent warps hold 0: ni_large_ctx clears them).
+// Every thread sums redundantly, so this sits on the serial path of an attempt: the tree is 4 dependent additions
+// where a running sum over 16 warps was 15.
 NI_DEV double ni_large_block_sum(const NiLargeCtx &c, double x, int parity) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+  constexpr int NW = NI_LARGE_MAX_THREADS / 32;
   double *part = c.part + parity * 32;
   if ((c.tid & 31) == 0) part[c.tid >> 5] = x;
   __syncthreads();
-  double s = part[0];
-  const int nw = c.T >> 5;
-  for (int w = 1; w < nw; ++w) s = __dadd_rn(s, part[w]);
-  return s;
+  double v[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) v[w] = part[w];
+#pragma unroll
+  for (int st = 1; st < NW; st <<= 1) {
+#pragma unroll
+    for (int k = 0; k + st < NW; k += 2 * st) v[k] = __dadd_rn(v[k], v[k + st]);
+  }
+  return v[0];
 }
 
 template <int CPT>
@@ -176,6 +185,8 @@ NI_DEV NiLargeCtx ni_large_ctx(const NiArgs &a, double *smem, int cpt, int total
   c.part = c.edge + 4 * NI_LARGE_MAX_THREADS;
   c.bcast = (long long *)(c.part + 64);
   c.ys = (double *)(c.bcast + 8);
+  for (int k = c.tid; k < 64; k += c.T) c.part[k] = 0.0;  // slots of absent warps stay zero (ni_large_block_sum)
+  __syncthreads();
   return c;
 }
 
@@ -386,41 +397,94 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       }
       ni_large_rhs<Rhs, CPT, FAST>(c, tn, yn, p, parity, kn);
       parity ^= 1;
+      // ---- error / scale and its sum of squares for the CPT components of this thread (_basic.py:166-169).
+      // Three passes over the components, each free of branches, so that the CPT dot products and the CPT quotients
+      // interleave: one component after the other (dot, tolerance test, operator `/` with its slow-path branch) is
+      // a chain of ~30 dependent FP64 operations per component and was a quarter of the kernel time on C5.  Strict
+      // arithmetic uses the guarded branch-free quotient of ni_math.cuh; a thread whose operands leave the guarded
+      // range (a denormal or non-finite error; a zero-error padding component is fine) redoes them with the operator.
       double sq = 0.0;
+      auto error_terms = [&](auto uniform) {
+        constexpr bool UNI = decltype(uniform)::value != 0;
+        double num[CPT], den[CPT], e[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        sv(Slots::slot(S), i) = kn[i];
-        const int j = ni_large_j<Rhs>(c, i);
-        const double ed = ni_dot_col<METHOD, S + 1, S + 1, false>([&](auto jj) {
-          if constexpr (decltype(jj)::value == S)
-            return kn[i];
-          else
-            return kget(jj, i);
-        });
-        double rt = a.rtol[0], at = a.atol[0];  // uniform tolerances come from the constant bank
-        if (!a.tol_uniform) {
-          rt = j < n ? __ldg(a.rtol_d + j) : 0.0;
-          at = j < n ? __ldg(a.atol_d + j) : 1.0;
-        } else if (!c.full && j >= n) {
-          rt = 0.0;
-          at = 1.0;
+        for (int i = 0; i < CPT; ++i) {
+          const double ed = ni_dot_col<METHOD, S + 1, S + 1, false>([&](auto jj) {
+            if constexpr (decltype(jj)::value == S)
+              return kn[i];
+            else
+              return kget(jj, i);
+          });
+          num[i] = __dmul_rn(ed, h);
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int j = ni_large_j<Rhs>(c, i);
+          double rt, at;
+          if constexpr (UNI) {  // uniform tolerances come from the constant bank
+            const bool pad = !c.full && j >= n;
+            rt = pad ? 0.0 : a.rtol[0];
+            at = pad ? 1.0 : a.atol[0];
+          } else {
+            const int jc = j < n ? j : 0;
+            rt = j < n ? __ldg(a.rtol_d + jc) : 0.0;
+            at = j < n ? __ldg(a.atol_d + jc) : 1.0;
+          }
+          const double big = fmax(fabs(y[i]), fabs(yn[i]));
+          den[i] = FAST ? fma(big, rt, at) : __dadd_rn(at, __dmul_rn(big, rt));
         }
         if constexpr (FAST) {
-          const double e = __dmul_rn(ed, __dmul_rn(h, ni_rcp_fast(fma(fmax(fabs(y[i]), fabs(yn[i])), rt, at))));
-          sq = fma(e, e, sq);
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            e[i] = __dmul_rn(num[i], ni_rcp_fast(den[i]));
+            sq = fma(e[i], e[i], sq);
+          }
         } else {
-          const double e = __dmul_rn(ed, h) / __dadd_rn(at, __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), rt));
-          sq = __dadd_rn(sq, __dmul_rn(e, e));
+          unsigned out = 0u;
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            out |= ni_div_out(num[i], den[i]);
+            e[i] = ni_div_core(num[i], den[i]);
+          }
+          if (out != 0u) {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) e[i] = num[i] / den[i];
+          }
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) sq = __dadd_rn(sq, __dmul_rn(e[i], e[i]));
+        }
+      };
+      if (a.tol_uniform)
+        error_terms(NiInt<1>{});
+      else
+        error_terms(NiInt<0>{});
+      // strict: the RMS norm; fast: the mean square (the controller then takes its 2K-th root, ni_pow_fast)
+      const double ssq = ni_large_block_sum(c, sq, parity & 1);
+      double en, pw;
+      bool ok, nan;
+      if constexpr (FAST) {
+        en = ssq / (double)n;
+        pw = ni_pow_fast<2 * (Tab::ORDER + 1)>(en);
+        ok = en < 1.0;
+        nan = !ok && !(en >= 1.0);
+      } else {
+        // uniform across the CTA: quotient, root and controller power branch-free under the guards, the operators
+        // otherwise (see ni_small_run_body)
+        const double msq = ni_div_core(ssq, (double)n);
+        en = ni_sqrt_core(msq);
+        pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(msq, en);
+        ok = (unsigned)__double2hiint(en) < 0x3ff00000u;
+        nan = false;
+        if ((ni_sqrt_out(msq) | ni_exp_out(ssq)) != 0u) {
+          en = sqrt(ssq / (double)n);
+          pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
+          ok = en < 1.0;
+          nan = !ok && !(en >= 1.0);
         }
       }
-      // strict: the RMS norm; fast: the mean square (the controller then takes its 2K-th root, ni_pow_fast)
-      const double msq = ni_large_block_sum(c, sq, parity & 1) / (double)n;
-      const double en = FAST ? msq : sqrt(msq);
       --att_left;
 
       // ---- controller + commit: uniform across the CTA
-      const bool ok = en < 1.0;
-      const bool nan = !ok && !(en >= 1.0);
       bool park = false;
       long long slot = -1;
       if (REC && ok) {
@@ -429,7 +493,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         slot = c.bcast[1];
         park = slot >= a.rec_cap;
       }
-      const double sp = __dmul_rn(0.9, FAST ? ni_pow_fast<2 * (Tab::ORDER + 1)>(en) : ni_pow_ctrl<Tab::ORDER + 1>(en));
+      const double sp = __dmul_rn(0.9, pw);
       double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
       if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
