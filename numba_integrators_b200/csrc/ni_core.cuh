@@ -48,7 +48,7 @@
 #endif
 
 #ifndef NI_LARGE_MAX_THREADS
-#define NI_LARGE_MAX_THREADS 512  // CTA-per-trajectory kernels (ni_large.cuh): threads per CTA
+#define NI_LARGE_MAX_THREADS 256  // CTA-per-trajectory kernels (ni_large.cuh): threads per CTA (<= 16 components each)
 #endif
 #define NI_LARGE_MAX_N 4096  // largest state dimension of the CTA-per-trajectory kernels
 

@@ -45,21 +45,42 @@ struct NiStencilBurgers {
   }
 };
 
-// Which stage vectors stay in registers: K0 always (read by every stage); K2 for RK45 (5 reads) when the CTA has
-// 512 threads x 128 registers.  With 1024 threads x 64 registers only K0 fits.
-#ifndef NI_LARGE_K2_IN_REG
-#define NI_LARGE_K2_IN_REG (NI_LARGE_MAX_THREADS <= 512)
+// Which stage vectors stay in registers: K0 always (read by every stage), plus the stages in NI_LARGE_KREG_MASK45 /
+// NI_LARGE_KREG_MASK23 (bit j = K_j).  A CTA of 256 threads x 255 registers keeps y, K0, K1, K2, K3, K5 and the stage
+// input / output of an n = 4096 system (16 components per thread) in registers -- K5 is born after the last read of
+// K1, so the two share registers -- and only K4 (3 reads per attempt) lives in shared memory.  Measured on C5
+// (n = 4096, RK45), accepted steps/s: 512 threads x 128 registers with K2 in registers 1.95e7; 256 x 255 with K2
+// 1.95e7, with K2 K3 2.08e7, with K1 K2 K3 2.11e7, with K1 K2 K3 K5 2.19e7 (K2 K3 K5: the same).
+#ifndef NI_LARGE_KREG_MASK45
+#define NI_LARGE_KREG_MASK45 (NI_LARGE_MAX_THREADS <= 256 ? 46 : NI_LARGE_MAX_THREADS <= 512 ? 4 : 0)
 #endif
+#ifndef NI_LARGE_KREG_MASK23
+#define NI_LARGE_KREG_MASK23 (NI_LARGE_MAX_THREADS <= 256 ? 6 : 0)
+#endif
+template <int METHOD>
+NI_HD constexpr bool ni_large_kreg(int j) {
+  return j > 0 && j < 8 && (((METHOD == NI_RK45 ? (NI_LARGE_KREG_MASK45) : (NI_LARGE_KREG_MASK23)) >> j) & 1);
+}
 template <int METHOD, int J>
 struct NiKInReg {
-  static constexpr bool value = (J == 0) || (NI_LARGE_K2_IN_REG && METHOD == NI_RK45 && J == 2);
+  static constexpr bool value = (J == 0) || ni_large_kreg<METHOD>(J);
+};
+// register array of stage vector J (meaningful when NiKInReg<METHOD, J> holds and J > 0), and how many there are
+template <int METHOD>
+struct NiLargeRegs {
+  NI_HD static constexpr int index(int j) {
+    int r = 0;
+    for (int k = 1; k < j; ++k) r += ni_large_kreg<METHOD>(k) ? 1 : 0;
+    return r;
+  }
+  static constexpr int COUNT = index(NiTab<METHOD>::S) > 0 ? index(NiTab<METHOD>::S) : 1;
 };
 // shared-memory slot of stage vector J (1..S-1; the new FSAL stage K_S never leaves registers) and the slot count
 template <int METHOD>
 struct NiLargeSlots {
   NI_HD static constexpr int slot(int j) {
     int s = 0;
-    for (int k = 1; k < j; ++k) s += (NI_LARGE_K2_IN_REG && METHOD == NI_RK45 && k == 2) ? 0 : 1;
+    for (int k = 1; k < j; ++k) s += ni_large_kreg<METHOD>(k) ? 0 : 1;
     return s;
   }
   static constexpr int KSLOTS = slot(NiTab<METHOD>::S), TOTAL = KSLOTS > 0 ? KSLOTS : 1;
@@ -84,6 +105,7 @@ struct NiLargeCtx {
   bool full;  // n == T * CPT: no padding components, masks are skipped
 };
 
+
 // Component index of local slot i.  Stencil kernels: CPT contiguous components per thread (neighbours in
 // registers).  Component kernels: strided ownership (tid, tid + T, ...): conflict-free staging of the stage vector.
 template <class Rhs>
@@ -95,9 +117,11 @@ NI_DEV int ni_large_j(const NiLargeCtx &c, int i) {
 }
 
 // neighbour exchange: returns y_{j0-1} and y_{j0+CPT} of this thread for the stage vector `v`.  Two staging buffers
-// alternate, so one CTA barrier per exchange is enough.  (Measured alternative: per-warp sequence flags +
-// __threadfence_block so that a warp only waits for its two neighbour warps -- 2.6x SLOWER than BAR.SYNC on C5: the
-// fences and spinning lanes cost more than the barrier stalls they remove.)
+// alternate, so one CTA barrier per exchange is enough.  Measured alternatives on C5: per-warp sequence flags +
+// __threadfence_block so that a warp only waits for its two neighbour warps -- 2.6x SLOWER than BAR.SYNC (the fences
+// and spinning lanes cost more than the barrier stalls they remove); a split barrier (mbarrier arrive after
+// publishing the edges, inner components, try_wait, edge components) -- 2 % slower (more live registers, and the
+// arrive / try_wait pair costs more than BAR.SYNC when the warps run in step anyway).
 template <int CPT>
 NI_DEV void ni_large_edges(const NiLargeCtx &c, const double (&v)[CPT], int parity, double &left, double &right) {
   double *eL = c.edge + (parity * 2 + 0) * NI_LARGE_MAX_THREADS, *eR = c.edge + (parity * 2 + 1) * NI_LARGE_MAX_THREADS;
@@ -110,7 +134,7 @@ NI_DEV void ni_large_edges(const NiLargeCtx &c, const double (&v)[CPT], int pari
 
 // dy for the CPT components of this thread; components >= n stay exactly zero
 template <class Rhs, int CPT, bool FAST = false>
-NI_DEV void ni_large_rhs(const NiLargeCtx &c, double t, const double (&v)[CPT], const double *p, int parity,
+NI_DEV void ni_large_rhs(NiLargeCtx &c, double t, const double (&v)[CPT], const double *p, int parity,
                          double (&out)[CPT]) {
   if constexpr (Rhs::COMPONENT) {
     // dense coupling: stage the whole vector in shared memory, every thread evaluates its own components from it
@@ -308,13 +332,14 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     }
     double t = a.t[idx], h_abs = a.h_abs[idx], step_h = a.step_size[idx];
     const double tb = a.t_bound[idx], dir = a.direction[idx];
-    double y[CPT], k0[CPT], k2[CPT], p[P > 0 ? P : 1];
+    double y[CPT], k0[CPT], kr[NiLargeRegs<METHOD>::COUNT][CPT], p[P > 0 ? P : 1];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
       const int j = ni_large_j<Rhs>(c, i);
       y[i] = j < n ? a.y[idx * n + j] : 0.0;
       k0[i] = j < n ? a.klast[idx * n + j] : 0.0;
-      k2[i] = 0.0;
+#pragma unroll
+      for (int r = 0; r < NiLargeRegs<METHOD>::COUNT; ++r) kr[r][i] = 0.0;
     }
 #pragma unroll
     for (int i = 0; i < P; ++i) p[i] = a.params[idx * P + i];
@@ -366,7 +391,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         if constexpr (j == 0)
           return k0[i];
         else if constexpr (NiKInReg<METHOD, j>::value)
-          return k2[i];
+          return kr[NiLargeRegs<METHOD>::index(j)][i];
         else
           return sv(Slots::slot(j), i);
       };
@@ -384,7 +409,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
 #pragma unroll
         for (int i = 0; i < CPT; ++i) {
           if constexpr (NiKInReg<METHOD, s>::value)
-            k2[i] = ks[i];
+            kr[NiLargeRegs<METHOD>::index(s)][i] = ks[i];
           else
             sv(Slots::slot(s), i) = ks[i];
         }
@@ -450,8 +475,15 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
 #pragma unroll
             for (int i = 0; i < CPT; ++i) e[i] = num[i] / den[i];
           }
+          // pairwise tree (log2 CPT dependent additions; the threads' sums are then combined by ni_large_block_sum)
 #pragma unroll
-          for (int i = 0; i < CPT; ++i) sq = __dadd_rn(sq, __dmul_rn(e[i], e[i]));
+          for (int i = 0; i < CPT; ++i) e[i] = __dmul_rn(e[i], e[i]);
+#pragma unroll
+          for (int st = 1; st < CPT; st <<= 1) {
+#pragma unroll
+            for (int k = 0; k + st < CPT; k += 2 * st) e[k] = __dadd_rn(e[k], e[k + st]);
+          }
+          sq = e[0];
         }
       };
       if (a.tol_uniform)

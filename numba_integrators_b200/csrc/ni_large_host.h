@@ -14,8 +14,8 @@ struct NiLargePlan {
 
 struct NiLargeKernels {  // every instantiation for one stencil RHS
   int P, Q;
-  const void *init[2][4];        // [method][log2 cpt]
-  const void *run[2][2][2][4];   // [method][advanced][record][log2 cpt]
+  const void *init[2][5];        // [method][log2 cpt]
+  const void *run[2][2][2][5];   // [method][advanced][record][log2 cpt]
 };
 const NiLargeKernels *ni_large_kernels_heat();
 const NiLargeKernels *ni_large_kernels_burgers();
