@@ -40,11 +40,12 @@
 #ifndef NI_BLOCK
 #define NI_BLOCK 128
 #endif
-// resident CTAs per SM the register allocator must allow for the run kernel: 6 x 128 threads (80 registers)
-// measured best for n <= 3 (+10 % over the unconstrained 90 registers / 5 CTAs on C3); larger systems keep
-// all their stage vectors in registers and take what they need
+// resident CTAs per SM the register allocator must allow for the run kernel.  n = 3 (Lorenz RK45 needs 94 registers):
+// 5 x 128 threads without spills beat 6 x 128 at 80 registers with a few (+3 % on C3; before the error-norm tail
+// became one basic block it was the other way round); n <= 2 fits 6 CTAs without spilling; larger systems keep all
+// their stage vectors in registers and take what they need
 #ifndef NI_MIN_BLOCKS
-#define NI_MIN_BLOCKS(n) ((n) <= 3 ? 6 : 1)
+#define NI_MIN_BLOCKS(n) ((n) <= 2 ? 6 : (n) == 3 ? 5 : 1)
 #endif
 
 #ifndef NI_LARGE_MAX_THREADS
@@ -668,12 +669,12 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         // dependent chains interleave (the operators' slow-path branches would serialise them); operands outside
         // the guards -- a zero, denormal or non-finite error -- redo the tail with the operators.
         double num[n], q[n];
-        unsigned out = 0u;  // some operand is outside the guarded ranges
+        NiDivGuard guard = ni_guard_begin();
 #pragma unroll
         for (int i = 0; i < n; ++i) {
           num[i] = __dmul_rn(ev[i], h);
           const double den = __dadd_rn(a.atol[i], __dmul_rn(ni_absmax(y[i], yn[i]), a.rtol[i]));
-          out |= ni_div_out(num[i], den);
+          ni_guard_add(guard, num[i], den);
           q[i] = ni_div_core(num[i], den);
           kn[i] = K[S][i];
         }
@@ -682,7 +683,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(q[i], q[i]));
         // acc / n (_aux.py:75): exact for n = 1, 2; Markstein for n = 3; the guard on ms below covers acc otherwise
         const double ms = n == 1 ? acc : n == 2 ? __dmul_rn(acc, 0.5) : n == 3 ? ni_div3(acc) : ni_div_core(acc, (double)n);
-        out |= ni_sqrt_out(ms);
+        const unsigned out = ni_guard_out(guard) | ni_sqrt_out(ms);  // some operand is outside the guarded ranges
         en = ni_sqrt_core(ms);
         pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
         en_lt1 = (unsigned)__double2hiint(en) < 0x3ff00000u;  // en > 0 here

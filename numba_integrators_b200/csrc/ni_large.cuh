@@ -446,10 +446,9 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         for (int i = 0; i < CPT; ++i) {
           const int j = ni_large_j<Rhs>(c, i);
           double rt, at;
-          if constexpr (UNI) {  // uniform tolerances come from the constant bank
-            const bool pad = !c.full && j >= n;
-            rt = pad ? 0.0 : a.rtol[0];
-            at = pad ? 1.0 : a.atol[0];
+          if constexpr (UNI) {  // uniform tolerances come from the constant bank; a padding component is 0 / atol
+            rt = a.rtol[0];
+            at = a.atol[0];
           } else {
             const int jc = j < n ? j : 0;
             rt = j < n ? __ldg(a.rtol_d + jc) : 0.0;
@@ -465,13 +464,13 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
             sq = fma(e[i], e[i], sq);
           }
         } else {
-          unsigned out = 0u;
+          NiDivGuard guard = ni_guard_begin();
 #pragma unroll
           for (int i = 0; i < CPT; ++i) {
-            out |= ni_div_out(num[i], den[i]);
+            ni_guard_add(guard, num[i], den[i]);
             e[i] = ni_div_core(num[i], den[i]);
           }
-          if (out != 0u) {
+          if (ni_guard_out(guard) != 0u) {
 #pragma unroll
             for (int i = 0; i < CPT; ++i) e[i] = num[i] / den[i];
           }
@@ -486,7 +485,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
           sq = e[0];
         }
       };
-      if (a.tol_uniform)
+      if (a.tol_uniform && (c.full || a.atol[0] > 0.0))  // (padding components need atol > 0: theirs is 0 / atol)
         error_terms(NiInt<1>{});
       else
         error_terms(NiInt<0>{});
@@ -502,12 +501,13 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       } else {
         // uniform across the CTA: quotient, root and controller power branch-free under the guards, the operators
         // otherwise (see ni_small_run_body)
-        const double msq = ni_div_core(ssq, (double)n);
+        // (n a power of two: the reciprocal is exact; a non-finite, zero or denormal ssq fails the guard on msq)
+        const double msq = (n & (n - 1)) == 0 ? __dmul_rn(ssq, 1.0 / (double)n) : ni_div_core(ssq, (double)n);
         en = ni_sqrt_core(msq);
         pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(msq, en);
         ok = (unsigned)__double2hiint(en) < 0x3ff00000u;
         nan = false;
-        if ((ni_sqrt_out(msq) | ni_exp_out(ssq)) != 0u) {
+        if (ni_sqrt_out(msq) != 0u) {
           en = sqrt(ssq / (double)n);
           pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
           ok = en < 1.0;
