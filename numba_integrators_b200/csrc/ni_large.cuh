@@ -454,7 +454,9 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
             rt = j < n ? __ldg(a.rtol_d + jc) : 0.0;
             at = j < n ? __ldg(a.atol_d + jc) : 1.0;
           }
-          const double big = fmax(fabs(y[i]), fabs(yn[i]));
+          // integer max of the magnitudes (no FP64 compare); a NaN operand gives a NaN scale where fmax would have
+          // dropped it, but then the error is NaN as well and the attempt ends in NI_ST_NONFINITE either way
+          const double big = FAST ? fmax(fabs(y[i]), fabs(yn[i])) : ni_absmax(y[i], yn[i]);
           den[i] = FAST ? fma(big, rt, at) : __dadd_rn(at, __dmul_rn(big, rt));
         }
         if constexpr (FAST) {
