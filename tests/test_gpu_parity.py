@@ -146,3 +146,58 @@ def test_fast_arithmetic_mode_meets_the_tolerance_bar(cfg, oracle):
     assert same.mean() >= 0.999, same.mean()
     assert np.mean(rel <= 1e-12) >= need, (np.mean(rel <= 1e-12), rel.max())
     assert np.all(s.t == w.t_bound) and np.all(s.status == 1)
+
+
+# ---- operands outside the guarded ranges of the branch-free error-norm tail (csrc/ni_math.cuh): the kernels must
+# fall back to the operators and still follow the oracle (zero error norm -> MAX_FACTOR, zero absolute tolerance with a
+# zero component -> 0 / 0 -> NaN -> NONFINITE, padding components of a CTA-per-trajectory system with atol = 0)
+def _against_oracle(oracle, name, method, y0, t_bound, params=None, rtol=1e-8, atol=1e-8, advanced=False, tol=1e-12):
+    f = ni.BuiltinRHS(name)
+    m = oracle.RK45 if method == 'RK45' else oracle.RK23
+    if advanced:
+        s = ni.Advanced(f.P, f.Q, getattr(ni, method))(f, 0.0, y0, params if f.P else None, t_bound, rtol=rtol, atol=atol)
+    else:
+        s = getattr(ni, method)(f(*params.T) if f.P else f, 0.0, y0, t_bound, rtol=rtol, atol=atol)
+    s.run()
+    ref = oracle.run_ensemble(name, m, 0.0, y0, t_bound, params=params, rtol=rtol, atol=atol, advanced=advanced)
+    assert np.array_equal(np.atleast_1d(s.status), ref['status']), (s.status, ref['status'])
+    assert np.array_equal(np.atleast_1d(s.n_accepted), ref['n_accepted'])
+    assert np.array_equal(np.atleast_1d(s.n_rejected), ref['n_rejected'])
+    fin = np.isfinite(ref['y'])
+    assert np.array_equal(np.isfinite(np.atleast_2d(s.y)), fin)
+    scale = max(np.max(np.abs(ref['y'][fin]), initial=0.0), 1e-300)
+    assert np.max(np.abs(np.atleast_2d(s.y)[fin] - ref['y'][fin]), initial=0.0) <= tol * scale
+    return s, ref
+
+
+@pytest.mark.parametrize('method', ['RK45', 'RK23'])
+def test_zero_error_norm_takes_the_operator_fallback(method, oracle):
+    # y == 0 stays 0 with an exactly zero error estimate: every attempt grows the step by MAX_FACTOR
+    y0 = np.zeros((5, 2))
+    y0[3] = (0.0, 1.0)                                  # a normal trajectory in the same warp
+    s, ref = _against_oracle(oracle, 'harmonic', method, y0, 3.0)
+    assert np.all(ref['n_rejected'][[0, 1, 2, 4]] == 0) and np.all(np.atleast_2d(s.y)[0] == 0.0)
+    _against_oracle(oracle, 'exponential', method, np.zeros((3, 1)), 2.0)
+
+
+def test_zero_absolute_tolerance_with_a_zero_component(oracle):
+    # scale = 0 + 0 * rtol = 0 and error 0: 0 / 0 = NaN in the reference, which then never terminates; the kernels
+    # (and the oracle) latch NONFINITE.  A second trajectory away from zero integrates normally with atol = 0.
+    y0 = np.array([[0.0, 0.0], [0.3, -0.7]])
+    s, ref = _against_oracle(oracle, 'harmonic', 'RK45', y0, 2.0, atol=0.0)
+    assert ref['status'][0] == 3 and ref['status'][1] == 1
+
+
+@pytest.mark.parametrize('n', [4096, 1000, 77])
+def test_large_system_fallbacks(n, oracle):
+    # rows: all-zero state (zero error: fallback of the CTA-wide root / power), a regular row, and -- for n that does
+    # not fill the CTA -- padding components whose scale must not become 0 / 0 when atol = 0
+    N = 3
+    x = (np.arange(n) + 1.0) / (n + 1.0)
+    y0 = np.zeros((N, n))
+    y0[1] = np.sin(np.pi * x)
+    y0[2] = 1.0 + 0.5 * np.cos(3 * np.pi * x)
+    k = np.array([[1.0], [0.7], [1.3]])
+    _against_oracle(oracle, 'heat1d', 'RK45', y0, 3.0, params=k, tol=1e-10)
+    # atol = 0: rows 1 and 2 only (row 0 would be 0 / 0)
+    _against_oracle(oracle, 'heat1d', 'RK45', y0[1:] + 2.0, 3.0, params=k[1:], atol=0.0, tol=1e-10)
