@@ -343,11 +343,12 @@ NI_DEV double ni_pow_init(double x) {
 // |nextafter(t, dir*inf) - t|  (_basic.py:139), for finite t.  Integer sign tests instead of FP64 compares: this
 // runs once per attempt in the branch-free hot loop.
 NI_DEV double ni_ulp_eps(double t, double dir) {
-  const long long b = __double_as_longlong(t), d = __double_as_longlong(dir);
-  const bool away = (b ^ d) >= 0;          // same sign bit: the neighbour towards dir*inf is further from zero
-  long long nb = away ? b + 1 : b - 1;
-  if ((b << 1) == 0) nb = (d & (long long)0x8000000000000000ULL) | 1LL;  // t == +-0: the smallest denormal
-  return fabs(__dadd_rn(__longlong_as_double(nb), -t));
+  const int th = __double2hiint(t), tl = __double2loint(t);
+  const int s = (th ^ __double2hiint(dir)) >> 31;  // 0: the neighbour towards dir*inf is further from zero; -1: nearer
+  const long long nb = __double_as_longlong(t) + (long long)(s | 1);
+  const double e = fabs(__dadd_rn(__longlong_as_double(nb), -t));
+  const bool zero = ((th << 1) | tl) == 0;         // t == +-0: the smallest denormal, whatever the direction
+  return zero ? __longlong_as_double(1LL) : e;
 }
 
 // Comparisons of the hot loop on the integer pipe (the FP64 pipe is the kernel's bound; a DSETP costs it as much as
@@ -517,7 +518,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   for (int i = 0; i < (P > 0 ? P : 1); ++i) p[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < (Q > 0 ? Q : 1); ++i) aux[i] = 0.0;
-  int nacc = 0, nrej = 0, status = NI_ST_RUNNING;
+  int nacc = 0, status = NI_ST_RUNNING;  // nacc: REC only (step number of a record)
   int att_left = 0, acc_left = 0;
   long long rc_next = 0, rc_end = 0;  // REC: this warp's reserved slot range [rc_next, rc_end)
 
@@ -537,8 +538,10 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
 #pragma unroll
           for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
           a.status[idx] = status;
-          a.n_acc[idx] = nacc;
-          a.n_rej[idx] = nrej;
+          // the two budgets are the counters: accepted = accepts used, rejected = counted attempts - accepted
+          const int n_accepted = max_acc - acc_left, n_counted = max_att - att_left;
+          a.n_acc[idx] += n_accepted;
+          a.n_rej[idx] += n_counted - n_accepted;
           a.running[idx] = last_accept ? 1 : 0;
           if (SP) a.step_rejected[idx] = srej ? 1 : 0;
           if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
@@ -583,8 +586,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
 #pragma unroll
           for (int i = 0; i < Q; ++i) aux[i] = a.aux[i * N + idx];
-          nacc = a.n_acc[idx];
-          nrej = a.n_rej[idx];
+          if (REC) nacc = a.n_acc[idx];  // the record log tags every record with its step number
           att_left = max_att;
           acc_left = max_acc;
           last_accept = false;
@@ -766,10 +768,9 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       }
 #pragma unroll
       for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
-      nacc += accepted ? 1 : 0;
-      nrej += (upd && !ok) ? 1 : 0;
-      acc_left -= accepted ? 1 : 0;
-      att_left -= upd ? 1 : 0;
+      if (REC) nacc += (int)accepted;
+      acc_left -= (int)accepted;
+      att_left -= (int)upd;
       last_accept = act ? accepted : last_accept;
       srej = upd ? !ok : srej;
       if (REC && accepted) {
