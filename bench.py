@@ -388,6 +388,17 @@ def main():
                                'frac': rec_bytes / (run_ms * 1e-3) / 1e9 / hbm, 'bytes_per_accepted_step':
                                w.record_bytes_per_step, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)'
                                if peaks.get('hbm_gbs') else 'fallback 6650 GB/s'}
+        if ens.kind and not record:  # CTA per trajectory (C5): the HBM side, compulsory traffic and what streaming would cost
+            hbm = peaks.get('hbm_gbs') or 6650.0
+            comp = N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13)
+            stream = 264.0 * n * att_rank  # stage s reads nnz_s + 1 vectors and writes 1, y_new + error 8
+            roofline['hbm'] = {'bound': 'hbm', 'achieved': comp / (run_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                               'frac': comp / (run_ms * 1e-3) / 1e9 / hbm,
+                               'note': 'compulsory traffic only (state in, state out): every stage vector stays in registers / '
+                                       'shared memory',
+                               'streaming_design_gbs': stream / (run_ms * 1e-3) / 1e9,
+                               'streaming_design_note': 'a kernel that streams the stage vectors through HBM moves 264 n bytes '
+                                                        'per attempt; at this throughput it would need this bandwidth'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
