@@ -7,9 +7,41 @@ from pathlib import Path
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+_t = time.perf_counter()
 import numba_integrators_b200 as ni  # noqa: E402
+t_import = time.perf_counter() - _t
 
 y0 = np.array((0., 1.))
+
+# The reference's own start-up benchmark (tests/benchmarking.py:20-87, published in tests/benchmarking.yaml:29-32 for
+# v0.3.1: import 268 ms, first initialisation 1.7 s, second 778 ms, first step 617 ms -- numba JIT).  Here: the
+# built-in RHS needs no compilation; a Python RHS is translated and compiled once with NVRTC (cached per process).
+
+
+def _f(t, y):
+    return np.array((y[1], -y[0]))
+
+
+def _startup(rhs, label):
+    t0 = time.perf_counter()
+    s = ni.RK45(rhs, 0.0, y0, t_bound=1, atol=1e-8, rtol=1e-8)
+    t1 = time.perf_counter()
+    s2 = ni.RK45(rhs, 0.0, y0, t_bound=1, atol=1e-8, rtol=1e-8)
+    t2 = time.perf_counter()
+    ni.step(s)
+    t3 = time.perf_counter()
+    ni.step(s)
+    t4 = time.perf_counter()
+    print(f'start-up, {label}: first initialisation {1e3 * (t1 - t0):.1f} ms, second {1e3 * (t2 - t1):.1f} ms, '
+          f'first step {1e3 * (t3 - t2):.2f} ms, second step {1e3 * (t4 - t3):.3f} ms')
+    del s2
+
+
+print(f'import numba_integrators_b200: {1e3 * t_import:.0f} ms (reference v0.3.1: 268 ms)')
+_startup(ni.rhs.harmonic, 'built-in RHS (includes CUDA context creation)')
+_startup(_f, 'Python RHS (AST -> CUDA snippet -> NVRTC)')
+_startup(_f, 'Python RHS again (module cache)')
+print('  reference v0.3.1 (numba JIT): first initialisation 1700 ms, second 778 ms, first step 617 ms')
 s = ni.RK45(ni.rhs.harmonic, 0.0, y0, t_bound=1, atol=1e-8, rtol=1e-8)
 while ni.step(s):
     pass
