@@ -52,6 +52,15 @@ while ni.step(s):
     n += 1
 dt = time.perf_counter() - t0
 print(f'README loop, lock-step ni.step from Python: {n} steps, {1e6 * dt / n:.1f} us/step (kernel launch + D2H per step)')
+s = ni.RK45(ni.rhs.harmonic, 0.0, y0, t_bound=200.0, atol=1e-8, rtol=1e-8)
+for _ in range(100):
+    ni.step(s)
+t0 = time.perf_counter()
+n = 0
+while ni.step(s):
+    n += 1
+dt = time.perf_counter() - t0
+print(f'long lock-step loop (CUDA graph from the 65th step on): {n} steps, {1e6 * dt / n:.1f} us/step')
 s = ni.RK45(ni.rhs.harmonic, 0.0, y0, t_bound=20000 * np.pi, atol=1e-8, rtol=1e-8)   # tests/profiling.py of the reference
 t0 = time.perf_counter()
 s.run()
