@@ -498,3 +498,31 @@ def test_branch_free_tail_arithmetic_matches_the_operators():
     for which in (2, 3):
         _lib.check(L.ni_devmath_check(0, which, n, 99 + which, ctypes.byref(bad)))
         assert 0 <= bad.value <= n * 5e-5, (which, bad.value)
+
+
+def test_long_lock_step_loop_uses_the_graph_path_and_matches_fast_forward():
+    """ni.step() switches to a captured CUDA graph after 64 calls on an ensemble (csrc/ni_b200.cu step_with_graph);
+    the graph must be re-captured when the launch arguments change (recording switched on mid-loop) and the result
+    must stay bit-identical to the fast-forward run."""
+    y0 = np.array([[0.0, 1.0], [0.3, -0.2], [1.0, 1.0]])
+    ref = ni.RK45(ni.rhs.harmonic, 0.0, y0, 30.0, rtol=1e-8, atol=1e-8)
+    ref.run()
+    s = ni.RK45(ni.rhs.harmonic, 0.0, y0, 30.0, rtol=1e-8, atol=1e-8)
+    k = 0
+    while ni.step(s):
+        k += 1
+        if k == 150:
+            ni.ff2t(s, 20.0)                    # t_bound lives in device memory: same arguments, same graph
+    assert k > 200
+    s2 = ni.RK45(ni.rhs.harmonic, 0.0, y0, 30.0, rtol=1e-8, atol=1e-8)
+    for _ in range(100):
+        ni.step(s2)
+    s2.record_enable(4096)                       # other kernel, other arguments: re-capture
+    while ni.step(s2):
+        pass
+    rec = s2.record_drain()
+    assert len(rec) == int(np.sum(s2.n_accepted)) - 300
+    assert np.array_equal(s2.y, ref.y) and np.array_equal(s2.t, ref.t)
+    assert np.array_equal(s2.n_accepted, ref.n_accepted)
+    # the ff2t leg changes the step sequence (SURVEY A.2-4), so only the end point is comparable
+    assert np.all(s.t == 30.0) and np.allclose(s.y, ref.y, rtol=1e-7, atol=1e-9)
