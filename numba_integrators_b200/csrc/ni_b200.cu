@@ -604,6 +604,8 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
   NI_TRY(dalloc(e, &a.step_size, sN))
   NI_TRY(dalloc(e, &a.y, sN * n))
   NI_TRY(dalloc(e, &a.klast, sN * n))
+  a.y_rows = nullptr;
+  if (m->kind == NI_KIND_SMALL && n > 1) NI_TRY(dalloc(e, &a.y_rows, sN * n))  // row-major mirror of y for the getters
   NI_TRY(dalloc(e, &a.aux, sN * Q))
   NI_TRY(dalloc(e, &a.params, sN * P))
   NI_TRY(dalloc(e, &a.t_bound, sN))
@@ -1084,7 +1086,9 @@ NI_API int ni_ensemble_get(ni_ensemble *e, int field, void *host_out) {
   CU(cudaSetDevice(e->device));
   const size_t N = (size_t)e->N;
   if (f.comps == 0) return NI_OK;
-  if (f.comps > 1 && e->mod.kind == NI_KIND_SMALL) {  // component-major on device -> rows
+  if (field == NI_F_Y && e->mod.kind == NI_KIND_SMALL && e->a.y_rows) {  // kept row-major by the kernels
+    CU(cudaMemcpyAsync(host_out, e->a.y_rows, N * f.comps * 8, cudaMemcpyDeviceToHost, e->stream));
+  } else if (f.comps > 1 && e->mod.kind == NI_KIND_SMALL) {  // component-major on device -> rows
     if (int rc = need_scratch(e, N * f.comps * 8)) return rc;
     ni_k_to_rows<<<grid_for((long long)N * f.comps), 256, 0, e->stream>>>((const double *)f.ptr, (double *)e->scratch, (long long)N, f.comps);
     CU(cudaGetLastError());

@@ -66,6 +66,8 @@
 struct NiArgs {
   long long N;
   double *t, *h_abs, *step_size, *y, *klast, *aux;
+  double *y_rows;               // small kernels: a row-major (N x n) copy of y kept current by init / retire, so that
+                                // the host reads the state without a transposition kernel; may be NULL
   double *params;
   double *t_bound, *direction;
   int *status, *n_acc, *n_rej;
@@ -471,6 +473,10 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
       a.y[i * N + idx] = y[i];
       a.klast[i * N + idx] = f0[i];
     }
+    if (a.y_rows) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) a.y_rows[idx * n + i] = y[i];
+    }
 #pragma unroll
     for (int i = 0; i < P; ++i) a.params[i * N + idx] = p[i];
 #pragma unroll
@@ -534,6 +540,10 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           for (int i = 0; i < n; ++i) {
             a.y[i * N + idx] = y[i];
             a.klast[i * N + idx] = kl[i];
+          }
+          if (a.y_rows) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) a.y_rows[idx * n + i] = y[i];
           }
 #pragma unroll
           for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
