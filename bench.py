@@ -377,7 +377,8 @@ def main():
                 roofline['traffic_source'] = tr['capture']
                 if 'fp64_pipe_busy' in tr:  # ncu: fraction of cycles the FP64 pipe was busy (same capture)
                     roofline['fp64_pipe_busy_ncu'] = tr['fp64_pipe_busy']
-                roofline['algorithmic_bytes'] = (N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13)
+                rows = 8 * n if (not ens.kind and n > 1) else 0  # row-major mirror of y written at retirement
+                roofline['algorithmic_bytes'] = (N * (8 * (2 * n + ens.P + ens.Q + 5) + 13 + 8 * (2 * n + ens.Q + 3) + 13 + rows)
                                                  + (w.record_bytes_per_step * acc_rank if record else 0))
         except (OSError, ValueError):
             pass
