@@ -512,7 +512,6 @@ struct ni_ensemble {
     cudaLibrary_t lib = nullptr;
     const void *k_run[2] = {nullptr, nullptr};
   };
-  std::vector<std::pair<std::string, CondKernels>> cond_cache;  // user predicates compiled for this ensemble
   // lock-step ni.step(): {clear the queue, run kernel with max_accepts = 1, queue -> pinned host} as one CUDA graph
   // from the 65th call on (the call is launch-bound: 37 us per step with direct launches, 25 us with the graph).
   // Re-captured whenever the kernel arguments, the kernel or the stream differ from the captured ones.
@@ -557,8 +556,6 @@ NI_API int ni_ensemble_destroy(ni_ensemble *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->allocs) cudaFree(p);
-  for (auto &c : e->cond_cache)
-    if (c.second.lib) cudaLibraryUnload(c.second.lib);
   if (e->scratch) cudaFree(e->scratch);
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   g_pinned.put(e->q_host);
@@ -938,37 +935,21 @@ NI_API int ni_ensemble_ff2t(ni_ensemble *e, double t_end, uint8_t *is_not_last) 
   return rc;
 }
 
+NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const double *cond_params, int n_params,
+                                    uint8_t *hit, int64_t *n_hit);
+
+// Built-in threshold predicates (ni.y_above(i) ...): generated as a one-line predicate body and compiled into a copy
+// of the run kernel like a user predicate; the threshold travels as cp[0], so one kernel per (kind, index) serves
+// every value.  The ahead-of-time kernels carry no predicate code (ni_core.cuh).
 NI_API int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double value, uint8_t *hit, int64_t *n_hit) {
   if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
   if (cond_kind < NI_COND_Y_GT || cond_kind > NI_COND_AUX_LT) return fail(NI_ERR_INVALID, "unknown predicate kind %d", cond_kind);
   const int lim = cond_kind <= NI_COND_Y_LT ? e->mod.n : e->mod.Q;
   if (index < 0 || index >= lim) return fail(NI_ERR_INVALID, "predicate index %d out of range [0, %d)", index, lim);
   if (e->mod.kind != NI_KIND_SMALL) return fail(NI_ERR_UNSUPPORTED, "ff2cond is implemented for the thread-per-trajectory kernels only");
-  CU(cudaSetDevice(e->device));
-  CU(cudaMemsetAsync(e->a.cond_hit, 0, (size_t)e->N, e->stream));
-  e->a.cond_kind = cond_kind;
-  e->a.cond_index = index;
-  e->a.cond_value = value;
-  int64_t unfinished = 0;
-  int rc = ni_ensemble_run(e, &unfinished);
-  e->a.cond_kind = 0;
-  if (rc != NI_OK) return rc;
-  if (hit || n_hit) {
-    std::vector<uint8_t> tmp;
-    uint8_t *dst = hit;
-    if (!dst) {
-      tmp.resize((size_t)e->N);
-      dst = tmp.data();
-    }
-    CU(cudaMemcpyAsync(dst, e->a.cond_hit, (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    if (n_hit) {
-      int64_t c = 0;
-      for (int64_t i = 0; i < e->N; ++i) c += dst[i] != 0;
-      *n_hit = c;
-    }
-  }
-  return NI_OK;
+  const bool on_y = cond_kind <= NI_COND_Y_LT, gt = cond_kind == NI_COND_Y_GT || cond_kind == NI_COND_AUX_GT;
+  const std::string body = std::string("  return ") + (on_y ? "y[" : "aux[") + std::to_string(index) + "] " + (gt ? ">" : "<") + " cp[0];";
+  return ni_ensemble_ff2cond_user(e, body.c_str(), &value, 1, hit, n_hit);
 }
 
 // ni.ff2cond with a user predicate: the body of
@@ -981,10 +962,12 @@ NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const
   if (e->mod.kind != NI_KIND_SMALL || e->mod.rhs_src.empty())
     return fail(NI_ERR_UNSUPPORTED, "user predicates are implemented for the thread-per-trajectory kernels only");
   CU(cudaSetDevice(e->device));
-  ni_ensemble::CondKernels *ck = nullptr;
-  for (auto &c : e->cond_cache)
-    if (c.first == cond_body) ck = &c.second;
-  if (!ck) {
+  // run kernels with a predicate compiled in, shared by every ensemble of the process (key: generated source +
+  // options); never unloaded -- a few hundred KB per distinct (RHS, method, predicate)
+  static std::mutex cond_mu;
+  static std::vector<std::pair<std::string, ni_ensemble::CondKernels>> cond_cache;
+  ni_ensemble::CondKernels found, *ck = nullptr;
+  {
     const ni_module &m = e->mod;
     const std::string M = m.method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = m.scipy ? "2" : m.advanced ? "1" : "0",
                       F = m.fast ? "true" : "false";
@@ -998,16 +981,24 @@ NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const
            "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", false, " + F + ">(a); }\n";
     src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
            "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true, " + F + ">(a); }\n";
-    ni_module tmp;
-    const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
     const std::string opts = m.fast ? "--fmad=true" : "--fmad=false";
-    if (int rc = compile_and_load(src, opts.c_str(), names, &tmp)) return rc;
-    ni_ensemble::CondKernels k;
-    k.lib = tmp.lib;
-    k.k_run[0] = tmp.k_run[0];
-    k.k_run[1] = tmp.k_run[1];
-    e->cond_cache.emplace_back(std::string(cond_body), k);
-    ck = &e->cond_cache.back().second;
+    const std::string key = opts + "\n" + src;
+    std::lock_guard<std::mutex> lock(cond_mu);
+    for (auto &c : cond_cache)
+      if (c.first == key) {
+        found = c.second;
+        ck = &found;
+      }
+    if (!ck) {
+      ni_module tmp;
+      const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
+      if (int rc = compile_and_load(src, opts.c_str(), names, &tmp)) return rc;
+      found.lib = tmp.lib;
+      found.k_run[0] = tmp.k_run[0];
+      found.k_run[1] = tmp.k_run[1];
+      cond_cache.emplace_back(key, found);
+      ck = &found;
+    }
   }
   CU(cudaMemsetAsync(e->a.cond_hit, 0, (size_t)e->N, e->stream));
   e->a.cond_kind = 5;

@@ -93,7 +93,7 @@ struct NiArgs {
   unsigned int *rec_traj, *rec_step;
   double *rec_t, *rec_y, *rec_aux;  // rec_y [n][rec_cap], rec_aux [Q][rec_cap]
   // ff2cond: built-in predicate parameters
-  int cond_kind;                // 0 none, 1 y[i] > c, 2 y[i] < c, 3 aux[i] > c, 4 aux[i] < c, 5 user predicate (NVRTC)
+  int cond_kind;                // 0: no predicate; != 0: ff2cond launch of a kernel compiled with a predicate
   int cond_index;
   double cond_value;
   unsigned char *cond_hit;
@@ -364,31 +364,16 @@ NI_DEV double ni_absmax(double a, double b) {
 }
 
 // ---------------------------------------------------------------- predicates (ff2cond)
+// The predicate of ni.ff2cond is compiled INTO a copy of the run kernel (NVRTC, ni_ensemble_ff2cond[_user]): the
+// generated translation unit defines NI_HAVE_USER_COND and ni_user_cond after this header.  The ahead-of-time kernels
+// carry no predicate code at all -- a run-time predicate switch cost the hot loop of every run ~15 issue slots per
+// attempt and forced y[] through local memory (dynamic component index).
 #ifdef NI_HAVE_USER_COND
-// user predicate of ff2cond, defined by the generated translation unit after this header
 __device__ __forceinline__ bool ni_user_cond(double t, const double *y, const double *aux, const double *cp);
-#endif
-
-template <int n, int Q>
-NI_DEV bool ni_cond_test(const NiArgs &a, double t, const double (&y)[n], const double *aux) {
-  if (a.cond_kind == 0) return false;
-#ifdef NI_HAVE_USER_COND
-  if (a.cond_kind == 5) return ni_user_cond(t, y, aux, a.cond_params);
+#define NI_COND 1
 #else
-  (void)t;
+#define NI_COND 0
 #endif
-  double v = 0.0;
-  if (a.cond_kind <= 2) {
-#pragma unroll
-    for (int i = 0; i < n; ++i)
-      if (i == a.cond_index) v = y[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-      if (i == a.cond_index) v = aux[i];
-  }
-  return (a.cond_kind & 1) ? v > a.cond_value : v < a.cond_value;
-}
 
 // ---------------------------------------------------------------- init kernel
 // RK.__init__ (_basic.py:203-242): FSAL seed K[-1] = f(t0, y0), direction, error exponent,
@@ -504,8 +489,13 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
 // registers with every commit masked off.
 template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
-  constexpr bool ADV = SEM >= 1, SP = SEM == 2;
+  constexpr bool ADV = SEM >= 1, SP = SEM == 2, COND = NI_COND != 0;
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
+  // The auxiliary output of an accepted step is only observable when the step is recorded, when a predicate reads it,
+  // or when the trajectory leaves the kernel.  Without record log and predicate it is therefore evaluated ONCE, at
+  // retirement, from the committed (t, y) -- the same function of the same operands as the FSAL evaluation that
+  // produced K[-1] (_advanced.py:181), hence the same bits -- instead of once per attempt.
+  constexpr bool LAZY_AUX = Q > 0 && !REC && !COND;
   using Tab = NiTab<METHOD>;
   constexpr int S = Tab::S;
   constexpr unsigned FULL = 0xffffffffu;
@@ -533,6 +523,8 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     if (__any_sync(FULL, need)) {
       if (need) {
         if (active) {  // retire: write the trajectory back
+          // fast-forward: the terminal step() call of `while step(): pass` (_basic.py:135-136) overwrites step_size
+          if (status == NI_ST_FINISHED) step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
           a.t[idx] = t;
           a.h_abs[idx] = h_abs;
           a.step_size[idx] = step_h;
@@ -545,11 +537,21 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
 #pragma unroll
             for (int i = 0; i < n; ++i) a.y_rows[idx * n + i] = y[i];
           }
-#pragma unroll
-          for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
-          a.status[idx] = status;
           // the two budgets are the counters: accepted = accepts used, rejected = counted attempts - accepted
           const int n_accepted = max_acc - acc_left, n_counted = max_att - att_left;
+          if constexpr (LAZY_AUX) {
+            // (t, y) changed in this residency <=> a step was accepted or the failure exit committed its attempt
+            if (n_accepted > 0 || status == NI_ST_FAILED) {
+              double kd[n];
+              Rhs::template eval<FAST>(t, y, p, kd, aux);
+#pragma unroll
+              for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
+          }
+          a.status[idx] = status;
           a.n_acc[idx] += n_accepted;
           a.n_rej[idx] += n_counted - n_accepted;
           a.running[idx] = last_accept ? 1 : 0;
@@ -571,7 +573,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
             break;
           }
           status = a.status[idx];
-          if (a.cond_kind != 0 && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
+          if (COND && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
           if (status != NI_ST_RUNNING) {
             if (status >= 0) a.running[idx] = 0;  // step() on a finished / failed solver returns False
             continue;
@@ -594,8 +596,10 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
           }
 #pragma unroll
           for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
+          if constexpr (!LAZY_AUX) {
 #pragma unroll
-          for (int i = 0; i < Q; ++i) aux[i] = a.aux[i * N + idx];
+            for (int i = 0; i < Q; ++i) aux[i] = a.aux[i * N + idx];
+          }
           if (REC) nacc = a.n_acc[idx];  // the record log tags every record with its step number
           att_left = max_att;
           acc_left = max_acc;
@@ -757,10 +761,14 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       const bool park = (REC && ok && slot >= a.rec_cap) || (act && sp_fail);
       const bool upd = act && !park;  // this attempt counts
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
-      const double sp = __dmul_rn(0.9, pw);
+      const double sp = __dmul_rn(NI_MC(0, 0.9), pw);
       // accepted: min(MAX_FACTOR, sp) (en == 0 saturates ni_pow_ctrl, i.e. MAX_FACTOR, :172); rejected:
       // max(MIN_FACTOR, sp).  sp > 0 and never NaN (ni_pow_ctrl saturates): integer-pipe comparisons
-      double fac = ok ? (ni_lt_pos(sp, 10.0) ? sp : 10.0) : (ni_lt_pos(0.2, sp) ? sp : 0.2);
+      // An accepted attempt has en < 1, i.e. sp > 0.9 > MIN_FACTOR, and a rejected one en >= 1, i.e. sp <= 0.9 <
+      // MAX_FACTOR: the other clamp is a no-op either way, so both are applied unconditionally.  10.0 has a zero low
+      // word: sp < 10 <=> hi(sp) < hi(10).
+      double fac = __double2hiint(sp) < 0x40240000 ? sp : 10.0;
+      fac = ni_lt_pos(0.2, fac) ? fac : 0.2;
       if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
       // :179-180: commits the REJECTED t, y (h_new, min_step >= +0; a NaN h_new implies `nan`)
@@ -774,14 +782,20 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         y[i] = take ? yn[i] : y[i];
-        kl[i] = newk ? kn[i] : kl[i];
+        // without record log and scipy semantics newk == act, and a lane without work does not care about its K[-1]
+        if constexpr (SP || REC)
+          kl[i] = newk ? kn[i] : kl[i];
+        else
+          kl[i] = kn[i];
       }
+      if constexpr (!LAZY_AUX) {
 #pragma unroll
-      for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
+        for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
+      }
       if (REC) nacc += (int)accepted;
       acc_left -= (int)accepted;
       att_left -= (int)upd;
-      last_accept = act ? accepted : last_accept;
+      last_accept = accepted;  // only read when the lane retires its trajectory, i.e. while `act`
       srej = upd ? !ok : srej;
       if (REC && accepted) {
         const long long c = a.rec_cap;
@@ -800,14 +814,15 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       if (REC && park && !sp_fail) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
       if (fail || (act && sp_fail)) status = NI_ST_FAILED;
       if (nan) status = NI_ST_NONFINITE;
-      if (a.cond_kind != 0 && accepted && ni_cond_test<n, Q>(a, t, y, aux)) {
+#if NI_COND
+      if (accepted && ni_user_cond(t, y, aux, a.cond_params)) {
         a.cond_hit[idx] = 1;
         parked = true;
         done = true;
       }
+#endif
       if (accepted && !done && reach) {  // t == t_bound now: the attempt was clipped to it or landed on it
-        // fast-forward: the terminal step() call of `while step(): pass` (_basic.py:135-136)
-        step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
+        // fast-forward: this was the last step (the retire path emulates the terminal step() call)
         status = NI_ST_FINISHED;
         last_accept = false;
         done = true;
