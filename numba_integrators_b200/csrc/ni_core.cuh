@@ -516,7 +516,11 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   for (int i = 0; i < (Q > 0 ? Q : 1); ++i) aux[i] = 0.0;
   int nacc = 0, status = NI_ST_RUNNING;  // nacc: REC only (step number of a record)
   int att_left = 0, acc_left = 0;
-  long long rc_next = 0, rc_end = 0;  // REC: this warp's reserved slot range [rc_next, rc_end)
+  // REC: this warp's reserved chunk of the record log: slots [rc_base + rc_off, rc_base + rc_len) are free.  The
+  // chunk start is 64-bit and changes once per chunk; the per-attempt bookkeeping runs on the 32-bit offsets.
+  long long rc_base = 0;
+  int rc_off = 0, rc_len = 0;
+  const unsigned lanes_below = (1u << lane) - 1u;
 
   for (;;) {
     // ================================================================ SERVICE (rare)
@@ -728,28 +732,26 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     // (lock-step ni.step, where a chunk would be abandoned after one use).  Slots of an abandoned chunk are
     // marked NI_REC_INVALID so that the drain can skip them.
     long long slot = -1;
+    bool rec_full = false;  // this lane's record does not fit into the log any more
     if (REC) {
       const unsigned m = __ballot_sync(FULL, ok);
-      if (m) {
-        const int cnt = __popc(m);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        const long long room = rc_end - rc_next;  // uniform across the warp
-        long long nb = rc_next;
-        if (cnt > room) {
-          const unsigned long long want = a.rec_chunk > 0 ? (unsigned long long)a.rec_chunk : (unsigned long long)(cnt - room);
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(a.rec_cursor, want);
-          nb = (long long)__shfl_sync(FULL, base, 0);
-        }
-        if (ok) slot = rank < room ? rc_next + rank : nb + (rank - room);
-        if (cnt > room) {
-          const long long want = a.rec_chunk > 0 ? a.rec_chunk : (long long)(cnt - room);
-          rc_next = nb + (cnt - room);
-          rc_end = nb + want < a.rec_cap ? nb + want : (nb < a.rec_cap ? a.rec_cap : nb);
-          if (rc_next > rc_end) rc_next = rc_end;
-        } else {
-          rc_next += cnt;
-        }
+      const int cnt = __popc(m), rank = __popc(m & lanes_below);
+      const int off = rc_off + rank;
+      if (rc_off + cnt <= rc_len) {  // the usual case: the chunk has room for every accepting lane (also cnt == 0)
+        slot = rc_base + off;        // < rec_cap by construction of rc_len
+        rc_off += cnt;
+      } else {  // warp-uniform: take the rest of the chunk, reserve the next one for the lanes that do not fit
+        const int room = rc_len - rc_off;
+        const long long want = a.rec_chunk > 0 ? a.rec_chunk : (long long)(cnt - room);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.rec_cursor, (unsigned long long)want);
+        const long long nb = (long long)__shfl_sync(FULL, base, 0);
+        slot = rank < room ? rc_base + off : nb + (rank - room);
+        rec_full = slot >= a.rec_cap;
+        const long long avail = a.rec_cap - nb;  // slots of the new chunk that exist
+        rc_base = nb;
+        rc_len = (int)(avail < 0 ? 0 : (avail < want ? avail : want));
+        rc_off = cnt - room < rc_len ? cnt - room : rc_len;
       }
     }
 
@@ -758,7 +760,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       const bool nan = act && en_nan;
       // park: log full -> undo this attempt (the state before an attempt is exactly t, y, h_abs, K[-1]);
       // scipy's too-small-step exit also commits nothing of the attempt
-      const bool park = (REC && ok && slot >= a.rec_cap) || (act && sp_fail);
+      const bool park = (REC && ok && rec_full) || (act && sp_fail);
       const bool upd = act && !park;  // this attempt counts
       // SAFETY * en ** exp; en == 0 gives MAX_FACTOR either way (:172)
       const double sp = __dmul_rn(NI_MC(0, 0.9), pw);
@@ -831,7 +833,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     }
   }
   if (REC) {  // slots reserved but never written
-    for (long long sidx = rc_next + lane; sidx < rc_end; sidx += 32) a.rec_traj[sidx] = NI_REC_INVALID;
+    for (int o = rc_off + (int)lane; o < rc_len; o += 32) a.rec_traj[rc_base + o] = NI_REC_INVALID;
   }
 }
 
