@@ -348,7 +348,8 @@ NI_DEV double ni_ulp_eps(double t, double dir) {
   const int th = __double2hiint(t), tl = __double2loint(t);
   const int s = (th ^ __double2hiint(dir)) >> 31;  // 0: the neighbour towards dir*inf is further from zero; -1: nearer
   const long long nb = __double_as_longlong(t) + (long long)(s | 1);
-  const double e = fabs(__dadd_rn(__longlong_as_double(nb), -t));
+  const double d = __dadd_rn(__longlong_as_double(nb), -t);
+  const double e = __hiloint2double(__double2hiint(d) & 0x7fffffff, __double2loint(d));  // fabs on the integer pipe
   const bool zero = ((th << 1) | tl) == 0;         // t == +-0: the smallest denormal, whatever the direction
   return zero ? __longlong_as_double(1LL) : e;
 }
@@ -635,7 +636,9 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     const double h_pre = h_abs;
     const bool sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt, commits nothing
     if (!SP && ni_lt_pos(a.max_step, h_abs)) h_abs = __dadd_rn(a.max_step, -eps);
-    double h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
+    // h_abs * direction (_advanced.py:163) with direction = +-1: a sign flip on the integer pipe, bit for bit the product
+    double h = (ADV || SP) ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
+                           : h_abs;
     double tn = __dadd_rn(t, h);
     bool reach;  // direction * (t_new - t_bound) >= 0: this attempt ends on t_bound
     {
@@ -703,11 +706,35 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
         for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(q[i], q[i]));
         // acc / n (_aux.py:75): exact for n = 1, 2; Markstein for n = 3; the guard on ms below covers acc otherwise
         const double ms = n == 1 ? acc : n == 2 ? __dmul_rn(acc, 0.5) : n == 3 ? ni_div3(acc) : ni_div_core(acc, (double)n);
+#ifdef NI_ABLATE
+        // timing experiments only (tools/exp_ablate.sh): every attempt is accepted with factor 1, and a prefix of the
+        // error tail is kept alive through a comparison that never holds
+        unsigned out = 0u;
+        double live;
+#if NI_ABLATE == 1   // no tail at all: the error estimate only
+        live = __dadd_rn(__dadd_rn(ev[0], ev[n - 1]), h);
+        en = 0.5;
+#elif NI_ABLATE == 2  // + quotients and mean square
+        live = ms;
+        en = 0.5;
+#elif NI_ABLATE == 3  // + square root
+        en = ni_sqrt_core(ms);
+        live = en;
+#else                 // + controller power (the whole tail, but the step size never changes)
+        en = ni_sqrt_core(ms);
+        live = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
+#endif
+        pw = __double2hiint(live) == 0x7ff12345 ? 2.0 : 1.0 / 0.9;
+        en_lt1 = true;
+        en_nan = false;
+        (void)guard;
+#else
         const unsigned out = ni_guard_out(guard) | ni_sqrt_out(ms);  // some operand is outside the guarded ranges
         en = ni_sqrt_core(ms);
         pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
         en_lt1 = (unsigned)__double2hiint(en) < 0x3ff00000u;  // en > 0 here
         en_nan = false;
+#endif
         if (act && out != 0u) {
 #pragma unroll
           for (int i = 0; i < n; ++i)

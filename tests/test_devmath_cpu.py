@@ -14,6 +14,7 @@ def test_controller_math_is_correctly_rounded():
         bad_mine, bad_libm, differ, n = res[name]
         assert bad_mine == 0, (name, bad_mine)
         assert res[name + ' ms'] == 0, (name, res[name + ' ms'])
+        assert res[name + ' ms seed'] == 0, (name, res[name + ' ms seed'])  # seed error of the MUFU unit emulated
         assert differ == bad_libm and differ <= 0.002 * n       # the only disagreements are glibc's misroundings
     assert res['div3'] == 0
     assert max(res['fast']) < 5e-15
