@@ -360,8 +360,11 @@ NI_DEV double ni_ulp_eps(double t, double dir) {
 NI_DEV bool ni_lt_pos(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 // max(|a|, |b|); differs from fmax(fabs(a), fabs(b)) only for NaN operands (it returns the NaN, fmax the number)
 NI_DEV double ni_absmax(double a, double b) {
-  const long long x = __double_as_longlong(a) & 0x7fffffffffffffffLL, y = __double_as_longlong(b) & 0x7fffffffffffffffLL;
-  return __longlong_as_double(x > y ? x : y);
+  // (the sign is cleared on the high WORD: nvcc turns a 64-bit `& 0x7fff...` back into an FP64-pipe |x|)
+  const unsigned ah = (unsigned)__double2hiint(a) & 0x7fffffffu, bh = (unsigned)__double2hiint(b) & 0x7fffffffu;
+  const unsigned long long x = ((unsigned long long)ah << 32) | (unsigned)__double2loint(a),
+                           y = ((unsigned long long)bh << 32) | (unsigned)__double2loint(b);
+  return __longlong_as_double((long long)(x > y ? x : y));
 }
 
 // ---------------------------------------------------------------- predicates (ff2cond)
@@ -488,8 +491,12 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
 // (store the retired state, pop the next trajectory from the queue, reload) only when some lane needs it --
 // about once per 18 iterations on C3.  Lanes without work keep executing the arithmetic on their stale
 // registers with every commit masked off.
-template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
-NI_DEV void ni_small_run_body(const NiArgs &a) {
+//
+// MAXS: the launch has a finite max_step.  With the default max_step = inf the clamp of _basic.py:146-147 can never
+// fire; compiled out it saves ten issue cycles per attempt, so ni_small_run_body carries both bodies and picks one per
+// launch (the scipy variant reads max_step elsewhere too and keeps the general body).
+template <class Rhs, int METHOD, int SEM, bool REC, bool FAST, bool MAXS>
+NI_DEV void ni_small_run_impl(const NiArgs &a) {
   constexpr bool ADV = SEM >= 1, SP = SEM == 2, COND = NI_COND != 0;
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
   // The auxiliary output of an accepted step is only observable when the step is recorded, when a predicate reads it,
@@ -635,7 +642,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
     // ---- one attempt (_basic.py:145-169)
     const double h_pre = h_abs;
     const bool sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt, commits nothing
-    if (!SP && ni_lt_pos(a.max_step, h_abs)) h_abs = __dadd_rn(a.max_step, -eps);
+    if (!SP && MAXS && ni_lt_pos(a.max_step, h_abs)) h_abs = __dadd_rn(a.max_step, -eps);
     // h_abs * direction (_advanced.py:163) with direction = +-1: a sign flip on the integer pipe, bit for bit the product
     double h = (ADV || SP) ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
                            : h_abs;
@@ -651,7 +658,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
       tn = clip ? tb : tn;
       if (clip || SP) {  // scipy recomputes h = t_new - t on every attempt
         h = __dadd_rn(tn, -t);
-        h_abs = fabs(h);
+        h_abs = __hiloint2double(__double2hiint(h) & 0x7fffffff, __double2loint(h));  // fabs on the integer pipe
       }
     }
     double en, pw, kn[n], yn[n], auxn[Q > 0 ? Q : 1];  // error norm (fast: its square), en ** error_exponent
@@ -862,6 +869,14 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   if (REC) {  // slots reserved but never written
     for (int o = rc_off + (int)lane; o < rc_len; o += 32) a.rec_traj[rc_base + o] = NI_REC_INVALID;
   }
+}
+
+template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
+NI_DEV void ni_small_run_body(const NiArgs &a) {
+  if (SEM != 2 && __double_as_longlong(a.max_step) == 0x7ff0000000000000LL)
+    ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, false>(a);
+  else
+    ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, true>(a);
 }
 
 // ---------------------------------------------------------------- kernel entry points

@@ -30,7 +30,8 @@ struct NiStencilHeat {
   template <bool FAST>
   NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
     using A = NiA<FAST>;
-    return A::mul(p[0], A::add(A::nmadd(2.0, yc, ym), yp));  // strict: (ym - 2*yc) + yp
+    // (ym - 2*yc) + yp.  2*yc is exact, so fma(-2, yc, ym) IS RN(ym - 2*yc), bit for bit, in one instruction
+    return A::mul(p[0], A::add(fma(-2.0, yc, ym), yp));
   }
 };
 // p = (nu/dx^2, 1/(2dx)): dy_j = p0 (y_{j-1} - 2 y_j + y_{j+1}) - (y_j p1)(y_{j+1} - y_{j-1})
@@ -40,7 +41,7 @@ struct NiStencilBurgers {
   template <bool FAST>
   NI_DEV static double eval(double, double ym, double yc, double yp, const double *p, int, int) {
     using A = NiA<FAST>;
-    const double diff = A::mul(p[0], A::add(A::nmadd(2.0, yc, ym), yp));
+    const double diff = A::mul(p[0], A::add(fma(-2.0, yc, ym), yp));  // exact 2*yc: see NiStencilHeat
     return A::nmadd(A::mul(yc, p[1]), A::sub(yp, ym), diff);  // diff - (yc*p1)*(yp - ym)
   }
 };
