@@ -154,7 +154,9 @@ int ni_ensemble_run_async(ni_ensemble *e); /* one launch, no host synchronisatio
 int ni_ensemble_sync(ni_ensemble *e);
 /* ni.ff2t (_API.py:27-39).  is_not_last: uint8[N] host buffer or NULL. */
 int ni_ensemble_ff2t(ni_ensemble *e, double t_end, uint8_t *is_not_last);
-/* ni.ff2cond (_API.py:41-49) with a built-in predicate NI_COND_*; hit: uint8[N] or NULL. */
+/* ni.ff2cond (_API.py:41-49) with a built-in threshold predicate NI_COND_* (y[index] or aux[index] against `value`);
+ * hit: uint8[N] or NULL.  Like a user predicate it is fused into a copy of the run kernel (NVRTC, first use of a
+ * (kind, index) pair per process; `value` is a kernel argument). */
 int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double value, uint8_t *hit, int64_t *n_hit);
 
 /* ni.ff2cond with a user predicate (_API.py:41-49 takes any njit callable): `cond_body` is the body of
