@@ -314,11 +314,14 @@ class Ensemble:
 
     def upload(self, t0, y0, parameters, t_bound):
         """Asynchronous host -> HBM copy of new inputs: y0 (N, n), parameters (N, P) row-major float64
-        buffers (numpy arrays or pinned torch tensors), t0 / t_bound scalars or (N,) buffers."""
+        buffers (numpy arrays or pinned torch tensors), t0 / t_bound scalars or (N,) buffers.  Buffers of another
+        dtype / layout are converted (numpy) or refused (torch); they are kept alive until the next `sync()`."""
         t0p, t0n = _buf(t0, self.N)
         tbp, tbn = _buf(t_bound, self.N)
-        self._keep = (t0p, tbp)  # scalars live in small arrays until the copy has been issued
-        check(self._L.ni_ensemble_upload(self._h, _ptr(t0p), int(t0n), _ptr(y0), _ptr(parameters) if self.P else None,
+        y0b = _host_buffer(y0, np.float64, self.N * self.n, 'y0')
+        parb = _host_buffer(parameters, np.float64, self.N * self.P, 'parameters') if self.P else None
+        self._keep = (t0p, tbp, y0b, parb)  # the copies are asynchronous: the sources must outlive them
+        check(self._L.ni_ensemble_upload(self._h, _ptr(t0p), int(t0n), _ptr(y0b), _ptr(parb) if self.P else None,
                                          _ptr(tbp), int(tbn)))
 
     def reset(self):
@@ -331,10 +334,22 @@ class Ensemble:
 
     def sync(self):
         check(self._L.ni_ensemble_sync(self._h))
+        self._keep = None
+
+    _FIELD_SHAPE = {_lib.F_T: ('f8', 1), _lib.F_H_ABS: ('f8', 1), _lib.F_STEP_SIZE: ('f8', 1), _lib.F_T_BOUND: ('f8', 1),
+                    _lib.F_DIRECTION: ('f8', 1), _lib.F_STATUS: ('i4', 1), _lib.F_N_ACCEPTED: ('i4', 1),
+                    _lib.F_N_REJECTED: ('i4', 1), _lib.F_RUNNING: ('u1', 1), _lib.F_COND_HIT: ('u1', 1)}
 
     def fetch(self, field, out):
-        """Device -> host copy of one field into a caller-owned buffer (numpy array / pinned tensor)."""
-        check(self._L.ni_ensemble_get(self._h, int(field), _ptr(out)))
+        """Device -> host copy of one field into a caller-owned buffer (numpy array / pinned tensor), which must be
+        C-contiguous and have the field's dtype and size (checked: the copy would otherwise overrun or misread it)."""
+        field = int(field)
+        if field in self._FIELD_SHAPE:
+            dt, comps = self._FIELD_SHAPE[field]
+        else:
+            dt, comps = 'f8', {_lib.F_Y: self.n, _lib.F_KLAST: self.n, _lib.F_AUX: self.Q, _lib.F_PARAMS: self.P}.get(field, 1)
+        buf = _host_buffer(out, np.dtype(dt), self.N * comps, f'fetch(field {field})', writable=True)
+        check(self._L.ni_ensemble_get(self._h, field, _ptr(buf)))
         return out
 
     # ------------------------------------------------------------------ recording
@@ -390,11 +405,37 @@ class Ensemble:
 
 
 def _ptr(x):
+    """Address of a host buffer already validated by `_host_buffer` / `_buf` (numpy array or torch tensor)."""
     if x is None:
         return None
     if hasattr(x, 'data_ptr'):  # torch tensor (e.g. pinned host memory)
         return _lib._vp(x.data_ptr())
-    return _lib._vp(np.ascontiguousarray(x).ctypes.data) if not isinstance(x, np.ndarray) else _lib._vp(x.ctypes.data)
+    return _lib._vp(x.ctypes.data)
+
+
+def _host_buffer(x, dtype, count, what, writable=False):
+    """A C-contiguous host buffer of exactly `count` elements of `dtype` backing `x`.
+
+    numpy input of another dtype / layout is converted (the caller keeps the result alive until the asynchronous copy
+    has completed); an output buffer (`writable`) and torch tensors cannot be converted behind the caller's back and
+    must already match."""
+    dtype = np.dtype(dtype)
+    if hasattr(x, 'data_ptr'):  # torch tensor
+        import torch
+        want = {np.dtype('f8'): torch.float64, np.dtype('i4'): torch.int32, np.dtype('u1'): torch.uint8}[dtype]
+        if x.dtype != want or not x.is_contiguous() or x.numel() != count or x.device.type != 'cpu':
+            raise ValueError(f'{what}: need a contiguous CPU tensor of {count} x {want}, got {tuple(x.shape)} {x.dtype} '
+                             f'on {x.device}{"" if x.is_contiguous() else " (not contiguous)"}')
+        return x
+    if writable:
+        if not (isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.c_contiguous and x.flags.writeable
+                and x.size == count):
+            raise ValueError(f'{what}: need a writable C-contiguous {dtype} array of {count} elements')
+        return x
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if a.size != count:
+        raise ValueError(f'{what}: expected {count} values, got {a.size}')
+    return a
 
 
 def _buf(v, N):

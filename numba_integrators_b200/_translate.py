@@ -316,11 +316,22 @@ class _Translator:
     # ---- statements
     def materialise(self, name, value):
         """Bind a Python name to C variables holding `value` (so later reassignment inside if/for works)."""
+        if getattr(self, 'rt_depth', 0) > 0 and isinstance(self.env.get(name), (int, tuple)) \
+                and not isinstance(self.env.get(name), bool):
+            # translate-time constants are folded into the expressions that use them: rebinding one under a run-time
+            # condition would silently take effect unconditionally
+            raise TranslationError(f'`{name}` holds a translate-time constant (an int or a tuple) and is reassigned '
+                                   f'inside a run-time `if`; write it as a float (e.g. `{name} = 2.0`) so that it '
+                                   'becomes a variable of the generated code')
         if isinstance(value, (int,)) and not isinstance(value, bool):
             self.env[name] = value
+            if getattr(self, 'rt_depth', 0) > 0:
+                self.rt_scoped[-1].add(name)  # a constant bound under a run-time condition dies with its branch
             return
         if isinstance(value, tuple):
             self.env[name] = value
+            if getattr(self, 'rt_depth', 0) > 0:
+                self.rt_scoped[-1].add(name)
             return
         if isinstance(value, Vec):
             names = Vec(f'v_{name}_{i}' for i in range(len(value)))
@@ -405,18 +416,34 @@ class _Translator:
                 return
             c = self.cond(test)
             self.lines.append(f'if {c} {{')
-            for st in node.body:
-                self.stmt(st)
+            self._runtime_branch(node.body)
             if node.orelse:
                 self.lines.append('} else {')
-                for st in node.orelse:
-                    self.stmt(st)
+                self._runtime_branch(node.orelse)
             self.lines.append('}')
             return
         if isinstance(node, ast.Return):
+            if getattr(self, 'rt_depth', 0) > 0:
+                # the outputs are evaluated once, after all statements: a return under a run-time condition would be
+                # hoisted out of it
+                self.err(node, '`return` inside a run-time `if` (select the value into a variable and return once)')
             self.ret(node)
             return
         self.err(node, f'unsupported statement {type(node).__name__}')
+
+    def _runtime_branch(self, body):
+        """Statements of one branch of a run-time `if`: translate-time constants first bound here are dropped again."""
+        self.rt_depth = getattr(self, 'rt_depth', 0) + 1
+        if not hasattr(self, 'rt_scoped'):
+            self.rt_scoped = []
+        self.rt_scoped.append(set())
+        try:
+            for st in body:
+                self.stmt(st)
+        finally:
+            for name in self.rt_scoped.pop():
+                self.env.pop(name, None)
+            self.rt_depth -= 1
 
     def _fold_cond(self, test):
         """True / False if the condition only involves compile-time numbers, else None."""

@@ -656,6 +656,10 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
     cudaGetLastError();
     nb = m->kind == NI_KIND_LARGE ? 1 : 4;
   }
+  if (const char *env = getenv("NI_B200_BLOCKS_PER_SM")) {  // experiments: fewer resident CTAs than fit
+    const int want = atoi(env);
+    if (want >= 1 && want < nb) nb = want;
+  }
   e->blocks_per_sm = nb;
   e->q_host = g_pinned.get();
   *out = e;

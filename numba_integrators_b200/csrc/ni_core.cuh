@@ -53,6 +53,10 @@
 #endif
 #define NI_LARGE_MAX_N 4096  // largest state dimension of the CTA-per-trajectory kernels
 
+#ifndef NI_LEAN
+#define NI_LEAN 1  // 0: every launch takes the general run body (A/B experiments)
+#endif
+
 #define NI_FLAG_REC_OVERFLOW 1ull
 #define NI_REC_INVALID 0xffffffffu  // rec_traj value of a reserved-but-unused record slot
 
@@ -367,6 +371,77 @@ NI_DEV double ni_absmax(double a, double b) {
   return __longlong_as_double((long long)(x > y ? x : y));
 }
 
+// ---------------------------------------------------------------- one attempt (shared by every run-kernel variant)
+// Stages, y_new, the FSAL evaluation at (tn, y_new), the error estimate, and -- strict arithmetic -- error / scale,
+// the RMS norm and the controller power as ONE basic block (_basic.py:151-169, :174/:178): the n quotients, the root
+// and the power are the guarded branch-free sequences of ni_math.cuh, so their dependent chains interleave (the
+// operators' slow-path branches would serialise them).  `out != 0` reports an operand outside the guarded ranges (a
+// zero, denormal or non-finite error: the caller redoes the tail with the operators from `num`).  Fast arithmetic:
+// `en` is the MEAN SQUARE error and the caller takes the controller power (ni_pow_fast*).
+// kl = K[0] = K[-1] of the previous attempt: stale after a rejection (_basic.py:151).
+template <class Rhs, int METHOD, bool FAST>
+NI_DEV void ni_rk_attempt(const NiArgs &a, double t, double tn, double h, const double (&y)[Rhs::N],
+                          const double (&kl)[Rhs::N], const double (&p)[Rhs::P > 0 ? Rhs::P : 1], double (&yn)[Rhs::N],
+                          double (&kn)[Rhs::N], double (&auxn)[Rhs::Q > 0 ? Rhs::Q : 1], double (&num)[Rhs::N],
+                          double &en, double &pw, bool &en_lt1, unsigned &out) {
+  constexpr int n = Rhs::N, Q = Rhs::Q;
+  using Tab = NiTab<METHOD>;
+  constexpr int S = Tab::S;
+  double K[S + 1][n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) K[0][i] = kl[i];
+  ni_static_for<1, S>([&](auto ss) {
+    constexpr int s = decltype(ss)::value;
+    double d[n], ys[n], auxd[Q > 0 ? Q : 1];
+    ni_dot<METHOD, s, s, n>(K, d);
+#pragma unroll
+    for (int i = 0; i < n; ++i) ys[i] = NiA<FAST>::madd(d[i], h, y[i]);
+    Rhs::template eval<FAST>(NiA<FAST>::madd(ni_cval<METHOD, 0, s>(), h, t), ys, p, K[s], auxd);
+  });
+  double d[n];
+  ni_dot<METHOD, S, S, n>(K, d);
+#pragma unroll
+  for (int i = 0; i < n; ++i) yn[i] = NiA<FAST>::madd(h, d[i], y[i]);
+  Rhs::template eval<FAST>(tn, yn, p, K[S], auxn);
+  double ev[n];
+  ni_dot<METHOD, S + 1, S + 1, n>(K, ev);
+  if constexpr (FAST) {
+    double msq = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double sc = fma(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i], a.atol[i]);
+      const double e = __dmul_rn(ev[i], __dmul_rn(h, ni_rcp_fast(sc)));
+      msq = fma(e, e, msq);
+      kn[i] = K[S][i];
+      num[i] = 0.0;
+    }
+    en = __dmul_rn(msq, 1.0 / n);  // error_norm**2 (same < 1, == 0, NaN tests)
+    pw = 0.0;
+    en_lt1 = false;
+    out = 0u;
+  } else {
+    double q[n];
+    NiDivGuard guard = ni_guard_begin();
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      num[i] = __dmul_rn(ev[i], h);
+      const double den = __dadd_rn(a.atol[i], __dmul_rn(ni_absmax(y[i], yn[i]), a.rtol[i]));
+      ni_guard_add(guard, num[i], den);
+      q[i] = ni_div_core(num[i], den);
+      kn[i] = K[S][i];
+    }
+    double acc = __dmul_rn(q[0], q[0]);
+#pragma unroll
+    for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(q[i], q[i]));
+    // acc / n (_aux.py:75): exact for n = 1, 2; Markstein for n = 3; the guard on ms below covers acc otherwise
+    const double ms = n == 1 ? acc : n == 2 ? __dmul_rn(acc, 0.5) : n == 3 ? ni_div3(acc) : ni_div_core(acc, (double)n);
+    out = ni_guard_out(guard) | ni_sqrt_out(ms);
+    en = ni_sqrt_core(ms);
+    pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
+    en_lt1 = (unsigned)__double2hiint(en) < 0x3ff00000u;  // en > 0 here
+  }
+}
+
 // ---------------------------------------------------------------- predicates (ff2cond)
 // The predicate of ni.ff2cond is compiled INTO a copy of the run kernel (NVRTC, ni_ensemble_ff2cond[_user]): the
 // generated translation unit defines NI_HAVE_USER_COND and ni_user_cond after this header.  The ahead-of-time kernels
@@ -661,102 +736,25 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
         h_abs = __hiloint2double(__double2hiint(h) & 0x7fffffff, __double2loint(h));  // fabs on the integer pipe
       }
     }
-    double en, pw, kn[n], yn[n], auxn[Q > 0 ? Q : 1];  // error norm (fast: its square), en ** error_exponent
-    bool en_lt1, en_nan;
-    {
-      double K[S + 1][n];
-#pragma unroll
-      for (int i = 0; i < n; ++i) K[0][i] = kl[i];  // K[0] = K[-1]: stale after a rejection (:151)
-      ni_static_for<1, S>([&](auto ss) {
-        constexpr int s = decltype(ss)::value;
-        double d[n], ys[n], auxd[Q > 0 ? Q : 1];
-        ni_dot<METHOD, s, s, n>(K, d);
-#pragma unroll
-        for (int i = 0; i < n; ++i) ys[i] = NiA<FAST>::madd(d[i], h, y[i]);
-        Rhs::template eval<FAST>(NiA<FAST>::madd(ni_cval<METHOD, 0, s>(), h, t), ys, p, K[s], auxd);
-      });
-      double d[n];
-      ni_dot<METHOD, S, S, n>(K, d);
-#pragma unroll
-      for (int i = 0; i < n; ++i) yn[i] = NiA<FAST>::madd(h, d[i], y[i]);
-      Rhs::template eval<FAST>(tn, yn, p, K[S], auxn);
-      double ev[n];
-      ni_dot<METHOD, S + 1, S + 1, n>(K, ev);
-      if constexpr (FAST) {
-        // mean square error instead of the RMS norm: the controller takes (en^2)^(-1/(2K)) (ni_pow_fast)
-        double msq = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          const double sc = fma(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i], a.atol[i]);
-          const double e = __dmul_rn(ev[i], __dmul_rn(h, ni_rcp_fast(sc)));
-          msq = fma(e, e, msq);
-          kn[i] = K[S][i];
-        }
-        en = __dmul_rn(msq, 1.0 / n);  // en holds error_norm**2 in fast mode (same < 1, == 0, NaN tests)
-      } else {
-        // error / scale, RMS norm and controller power (_basic.py:166-169, :174/:178) as ONE basic block: the n
-        // quotients, the root and the power are the guarded branch-free sequences of ni_math.cuh, so their
-        // dependent chains interleave (the operators' slow-path branches would serialise them); operands outside
-        // the guards -- a zero, denormal or non-finite error -- redo the tail with the operators.
-        double num[n], q[n];
-        NiDivGuard guard = ni_guard_begin();
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-          num[i] = __dmul_rn(ev[i], h);
-          const double den = __dadd_rn(a.atol[i], __dmul_rn(ni_absmax(y[i], yn[i]), a.rtol[i]));
-          ni_guard_add(guard, num[i], den);
-          q[i] = ni_div_core(num[i], den);
-          kn[i] = K[S][i];
-        }
-        double acc = __dmul_rn(q[0], q[0]);
-#pragma unroll
-        for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(q[i], q[i]));
-        // acc / n (_aux.py:75): exact for n = 1, 2; Markstein for n = 3; the guard on ms below covers acc otherwise
-        const double ms = n == 1 ? acc : n == 2 ? __dmul_rn(acc, 0.5) : n == 3 ? ni_div3(acc) : ni_div_core(acc, (double)n);
-#ifdef NI_ABLATE
-        // timing experiments only (tools/exp_ablate.sh): every attempt is accepted with factor 1, and a prefix of the
-        // error tail is kept alive through a comparison that never holds
-        unsigned out = 0u;
-        double live;
-#if NI_ABLATE == 1   // no tail at all: the error estimate only
-        live = __dadd_rn(__dadd_rn(ev[0], ev[n - 1]), h);
-        en = 0.5;
-#elif NI_ABLATE == 2  // + quotients and mean square
-        live = ms;
-        en = 0.5;
-#elif NI_ABLATE == 3  // + square root
-        en = ni_sqrt_core(ms);
-        live = en;
-#else                 // + controller power (the whole tail, but the step size never changes)
-        en = ni_sqrt_core(ms);
-        live = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
-#endif
-        pw = __double2hiint(live) == 0x7ff12345 ? 2.0 : 1.0 / 0.9;
-        en_lt1 = true;
-        en_nan = false;
-        (void)guard;
-#else
-        const unsigned out = ni_guard_out(guard) | ni_sqrt_out(ms);  // some operand is outside the guarded ranges
-        en = ni_sqrt_core(ms);
-        pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
-        en_lt1 = (unsigned)__double2hiint(en) < 0x3ff00000u;  // en > 0 here
-        en_nan = false;
-#endif
-        if (act && out != 0u) {
-#pragma unroll
-          for (int i = 0; i < n; ++i)
-            ev[i] = num[i] / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
-          en = ni_rms<n>(ev);
-          pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
-          en_lt1 = en < 1.0;
-          en_nan = en != en;
-        }
-      }
-    }
+    double en, pw, kn[n], yn[n], auxn[Q > 0 ? Q : 1], num[n];  // error norm (fast: its square), en ** error_exponent
+    bool en_lt1, en_nan = false;
+    unsigned out;
+    ni_rk_attempt<Rhs, METHOD, FAST>(a, t, tn, h, y, kl, p, yn, kn, auxn, num, en, pw, en_lt1, out);
     if constexpr (FAST) {
       pw = ni_pow_fast<2 * (Tab::ORDER + 1)>(en);
       en_lt1 = en < 1.0;
       en_nan = en != en;
+    } else {
+      if (act && out != 0u) {  // an operand outside the guarded ranges: the tail again, with the operators
+        double ev[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+          ev[i] = num[i] / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+        en = ni_rms<n>(ev);
+        pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
+        en_lt1 = en < 1.0;
+        en_nan = en != en;
+      }
     }
     const bool ok = act && en_lt1 && !sp_fail;
 
@@ -871,12 +869,280 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
   }
 }
 
+// ---------------------------------------------------------------- run kernel, lean variant: cold block
+// Cold block of the lean run body: the attempt of this lane needs one of the rarely needed pieces of the controller --
+// the NaN latch (the reference would spin forever: status NONFINITE) or the step-size floor of the failure exit
+// (_basic.py:179-180) -- recomputed with the general formulas of ni_small_run_impl.  Out of line and
+// by value, so that the hot loop pays one predicated branch for it.  flags in: 1 = accepted, 2 = error norm is NaN;
+// out: 1 = accepted, 4 = failure exit (commit the rejected t, y), 8 = leave with `status`.
+struct NiLeanCold {
+  double h_new;
+  int flags, status;
+};
+static __device__ __noinline__ NiLeanCold ni_lean_cold(double t, double dir, double h_abs, double pw, int flags) {
+  const bool ok = (flags & 1) != 0, nan = (flags & 2) != 0;
+  const double sp = __dmul_rn(0.9, pw);
+  const double fac = fmax(0.2, fmin(10.0, sp));  // en == 0 saturates the power, i.e. MAX_FACTOR (:172)
+  NiLeanCold r;
+  r.h_new = nan ? h_abs : __dmul_rn(h_abs, fac);
+  const double min_step = __dmul_rn(8.0, ni_ulp_eps(t, dir));
+  const bool fail = !ok && !nan && r.h_new < min_step;  // :179-180
+  r.status = nan ? NI_ST_NONFINITE : fail ? NI_ST_FAILED : NI_ST_RUNNING;
+  r.flags = (ok && !nan ? 1 : 0) | (fail ? 4 : 0) | (fail || nan ? 8 : 0);
+  return r;
+}
+
+// ---------------------------------------------------------------- run kernel, lean variant
+// The same algorithm for the launches that need no per-attempt bookkeeping: reference semantics (SEM 0 / 1), no record
+// log, no predicate, max_step = inf, no attempt or accept budget (fast-forward; lock-step ni.step takes the general
+// body).  This is every benchmark launch but C2's.
+//
+// Why a second body: the thread-per-trajectory kernel is bound by REGISTER-FILE READ BANDWIDTH, not by the FP64 pipe
+// (tools/micro/fp64_shadow.cu, profiles/r02_issue_model.txt: a scheduler reads two 32-bit register operands per lane
+// per cycle; an FP64 instruction with two 64-bit register sources uses all of it for its two pipe cycles, so every
+// register operand of every other instruction adds half a cycle).  The general body above spends ~160 such operands per
+// attempt on selects, 64-bit integer compares and counters.  Here everything that is not needed on the usual path
+// is moved to places that run rarely:
+//  * step entry (_basic.py:139-156: 8 ulp(t) floor, t + h, clip to t_bound) is evaluated EXACTLY in the service branch
+//    for a trajectory that is loaded, or whose last attempt raised one of two conservative integer tests -- "t + h may
+//    have reached t_bound" (a monotone key of the high word of t + h against the key of t_bound, 2 instructions) and
+//    "h_abs may be below 8 ulp(t)" (high word of h_abs against a power-of-two bound from the exponent of t, 1
+//    instruction); otherwise the entry is h = +-h_abs, tn = t + h, bit for bit what the exact entry computes when
+//    neither clamp applies;
+//  * the failure exit (:179-180) and the NaN latch live in an out-of-line cold block behind the second conservative
+//    test;
+//  * attempts are counted by a warp-uniform iteration counter (rejected = iterations in residency - accepted), status /
+//    step_size / running are derived at retirement, lanes without work are not masked: they run on benign values and
+//    cannot raise a flag.
+template <class Rhs, int METHOD, bool ADV, bool FAST>
+NI_DEV void ni_small_run_lean(const NiArgs &a) {
+  constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
+  using Tab = NiTab<METHOD>;
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long N = a.N;
+  const unsigned lane = threadIdx.x & 31u;
+
+  long long idx = 0;
+  bool active = false, exhausted = false, svc = true;
+  double t = 0, h_abs = 0, tb = 0, dir = 1, tn = 0, step_h = 0;
+  double y[n], kl[n], p[P > 0 ? P : 1];
+#pragma unroll
+  for (int i = 0; i < n; ++i) y[i] = kl[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < (P > 0 ? P : 1); ++i) p[i] = 0.0;
+  int status = NI_ST_RUNNING, nacc = 0;
+  unsigned iter = 0, it0 = 0;  // hot-loop passes of this warp; the pass count at which the lane's trajectory was loaded
+  int kx = 0, tbk = 0x7fffffff;  // reach key: (hi(tn) ^ kx) >= tbk  <=  direction * (tn - t_bound) >= 0
+  int xs = 0;                    // hi(h_abs) <u xs  <=  h_abs may be below 8 ulp(t) of this or the next step
+
+  for (;;) {
+    // ================================================================ SERVICE (rare)
+    if (__any_sync(FULL, svc)) {
+      // exit: the cold block latched a failure, or the last accepted step ended on t_bound (the reference's own test
+      // at the top of its next step() call, _basic.py:135)
+      if (active && (status != NI_ST_RUNNING || __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0)) {
+        const int n_attempts = (int)(iter - it0);
+        if (status == NI_ST_RUNNING) {
+          status = NI_ST_FINISHED;
+          // the terminal step() call of `while step(): pass` (_basic.py:135-136) overwrites step_size
+          step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
+        }
+        a.t[idx] = t;
+        a.h_abs[idx] = h_abs;
+        a.step_size[idx] = step_h;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          a.y[i * N + idx] = y[i];
+          a.klast[i * N + idx] = kl[i];
+        }
+        if (a.y_rows) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) a.y_rows[idx * n + i] = y[i];
+        }
+        if constexpr (Q > 0) {
+          // the auxiliary output is the one of the FSAL evaluation at the committed (t, y) (_advanced.py:181): same
+          // function, same operands, same bits, evaluated once here instead of once per attempt
+          if (nacc > 0 || status == NI_ST_FAILED) {
+            double kd[n], aux[Q];
+            Rhs::template eval<FAST>(t, y, p, kd, aux);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) a.aux[i * N + idx] = aux[i];
+          }
+        }
+        a.status[idx] = status;
+        a.n_acc[idx] += nacc;
+        a.n_rej[idx] += n_attempts - nacc;
+        a.running[idx] = 0;
+        active = false;
+      }
+      // refill: pop trajectories (warp-aggregated) until one is runnable or the queue is empty
+      while (!active && !exhausted) {
+        const unsigned grp = __activemask();
+        const int leader = __ffs(grp) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        idx = (long long)(base + __popc(grp & ((1u << lane) - 1u)));
+        if (idx >= N) {
+          exhausted = true;
+          break;
+        }
+        status = a.status[idx];
+        if (status != NI_ST_RUNNING) {
+          a.running[idx] = 0;  // step() on a finished / failed solver returns False
+          continue;
+        }
+        t = a.t[idx];
+        h_abs = a.h_abs[idx];
+        tb = a.t_bound[idx];
+        dir = a.direction[idx];
+        if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached (_basic.py:135-136)
+          a.step_size[idx] = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
+          a.status[idx] = NI_ST_FINISHED;
+          a.running[idx] = 0;
+          continue;
+        }
+        step_h = a.step_size[idx];
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          y[i] = a.y[i * N + idx];
+          kl[i] = a.klast[i * N + idx];
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
+        // reach key of this trajectory: hi(tn) ^ kx is monotone in dir * tn over the sign regime in which t_bound can
+        // be reached, and compares as "reached" outside it
+        const int tbh = __double2hiint(tb);
+        if (__double2hiint(dir) >= 0) {
+          kx = tbh >= 0 ? 0 : 0x7fffffff;
+        } else {
+          kx = tbh < 0 ? (int)0x80000000 : -1;
+        }
+        tbk = tbh ^ kx;
+        nacc = 0;
+        it0 = iter;
+        active = true;
+      }
+      if (active) {
+        // ---- exact step entry (_basic.py:139-156) of the coming attempt
+        const double eps = ni_ulp_eps(t, dir);
+        const double min_step = __dmul_rn(8.0, eps);
+        h_abs = ni_lt_pos(h_abs, min_step) ? min_step : h_abs;
+        const double h = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
+                             : h_abs;
+        tn = __dadd_rn(t, h);
+        const double dtb = __dadd_rn(tn, -tb);
+        const bool zero = ((__double2hiint(dtb) << 1) | __double2loint(dtb)) == 0;
+        const bool same = (__double2hiint(dtb) ^ __double2hiint(dir)) >= 0;
+        if (zero || same) {  // direction * (t_new - t_bound) >= 0: this attempt ends on t_bound
+          tn = tb;
+          // (the clipped step t_bound - t has the sign of `direction`: h below is again +-h_abs)
+          h_abs = fabs(__dadd_rn(tn, -t));
+        }
+        const int xe = (__double2hiint(t) & 0x7ff00000) - (46 << 20);
+        xs = xe > 0x00100000 ? xe : 0x00100000;
+      } else {
+        // a lane without work keeps executing the arithmetic: give it values that raise no flag
+        t = 0.0;
+        h_abs = 0.0;
+        tn = 0.0;
+        tb = 0.0;
+        kx = 0;
+        tbk = 0x7fffffff;
+        xs = 0;
+      }
+      if (__all_sync(FULL, !active)) break;
+    }
+
+    // ================================================================ HOT: one attempt for every lane
+    // h = h_abs * direction (_advanced.py:163; a sign flip: direction = +-1) or h_abs (_basic.py:148); also after a
+    // clip to t_bound, where h_abs = |t_bound - t|
+    const double h = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
+                         : h_abs;
+    double en, pw, kn[n], yn[n], auxn[Q > 0 ? Q : 1], num[n];
+    bool ok;
+    unsigned out;
+    ni_rk_attempt<Rhs, METHOD, FAST>(a, t, tn, h, y, kl, p, yn, kn, auxn, num, en, pw, ok, out);
+    bool nan = false;
+    if constexpr (FAST) {
+      // (en holds the mean square error) the root without its range checks; outside [2^-100, 2^100) or NaN: redone
+      pw = ni_pow_fast_core<2 * (Tab::ORDER + 1)>(en);
+      ok = (unsigned)__double2hiint(en) < 0x3ff00000u;
+      if (active && (unsigned)(__double2hiint(en) - 0x39b00000) >= (0x46300000u - 0x39b00000u)) {
+        pw = ni_pow_fast<2 * (Tab::ORDER + 1)>(en);
+        ok = en < 1.0;
+        nan = en != en;
+      }
+    } else {
+      if (active && out != 0u) {  // an operand outside the guarded ranges: the tail again, with the operators
+        double ev[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+          ev[i] = num[i] / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
+        en = ni_rms<n>(ev);
+        pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
+        ok = en < 1.0;
+        nan = en != en;
+      }
+    }
+    // ---- controller + commit (_basic.py:171-180)
+    // SAFETY * en ** exp > 0 and never NaN here; both clamps unconditionally (an accepted attempt has factor > 0.9 >
+    // MIN_FACTOR, a rejected one <= 0.9 < MAX_FACTOR), on the integer pipe: 10.0 has a zero low word, so
+    // sp >= 10 <=> hi(sp) >= hi(10); sp < 0.2 is a 64-bit integer compare of non-negative doubles
+    const double sp = __dmul_rn(NI_MC(0, 0.9), pw);
+    double fac = __double2hiint(sp) >= 0x40240000 ? 10.0 : sp;
+    fac = ni_lt_pos(fac, 0.2) ? 0.2 : fac;
+    double h_new = __dmul_rn(h_abs, fac);
+    bool fail = false, cold = false;
+    if (active && (nan || (unsigned)__double2hiint(h_new) < (unsigned)xs)) {
+      const NiLeanCold c = ni_lean_cold(t, dir, h_abs, pw, (ok ? 1 : 0) | (nan ? 2 : 0));
+      h_new = c.h_new;
+      ok = (c.flags & 1) != 0;
+      fail = (c.flags & 4) != 0;
+      if (c.flags & 8) {
+        status = c.status;
+        step_h = h;  // step_size of the exit
+      }
+      cold = true;  // the coming step entry is evaluated exactly in the service branch (8 ulp floor)
+    }
+    const bool take = ok || fail;
+    t = take ? tn : t;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      y[i] = take ? yn[i] : y[i];
+      kl[i] = kn[i];  // also after a rejection: the stale FSAL stage
+    }
+    h_abs = h_new;
+    nacc += (int)ok;
+    ++iter;
+    // ---- fast step entry of the next attempt: exact unless one of the conservative tests sends the lane to the
+    // service branch.  A step that ended on t_bound raises the reach test by itself (t == t_bound now).
+    {
+      const int xe = (__double2hiint(t) & 0x7ff00000) - (46 << 20);
+      xs = xe > 0x00100000 ? xe : 0x00100000;
+      const double hn = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
+                            : h_abs;
+      tn = __dadd_rn(t, hn);
+      svc = cold || (__double2hiint(tn) ^ kx) >= tbk;
+    }
+  }
+}
+
 template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
-  if (SEM != 2 && __double_as_longlong(a.max_step) == 0x7ff0000000000000LL)
-    ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, false>(a);
-  else
-    ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, true>(a);
+  const bool no_max_step = __double_as_longlong(a.max_step) == 0x7ff0000000000000LL;
+  if constexpr (NI_LEAN && SEM != 2 && !REC && NI_COND == 0) {
+    // fast-forward without an attempt budget and with max_step = inf; lock-step ni.step takes the general body
+    if (no_max_step && a.max_attempts >= 0x7fffffffLL && a.max_accepts >= 0x7fffffffLL)
+      ni_small_run_lean<Rhs, METHOD, SEM == 1, FAST>(a);
+    else
+      ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, true>(a);
+  } else {
+    if (SEM != 2 && no_max_step)
+      ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, false>(a);
+    else
+      ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, true>(a);
+  }
 }
 
 // ---------------------------------------------------------------- kernel entry points

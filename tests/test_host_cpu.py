@@ -95,3 +95,28 @@ def test_workload_prefix_property_and_shards():
     assert np.allclose(mu, 0.1 + 19.9 * np.arange(8) / 7)     # interleaved shards cover the sweep
     h = wl.c5_heat(N=2, n=64)
     assert h.y0.shape == (2, 64) and h.params.shape == (2, 1)
+
+
+def test_host_buffer_validation():
+    """upload() / fetch() hand raw addresses to asynchronous copies: every buffer is checked (dtype, contiguity, size)
+    and converted inputs are returned so that the caller can keep them alive (a temporary's address
+    used to reach cudaMemcpyAsync)."""
+    hb = _solver._host_buffer
+    a = np.arange(12, dtype=np.float64).reshape(4, 3)
+    assert hb(a, np.float64, 12, 'y0') is a  # already right: no copy
+    for bad in (a.astype(np.float32), np.asfortranarray(a), a[:, ::-1], a.tolist()):
+        b = hb(bad, np.float64, 12, 'y0')
+        assert b.dtype == np.float64 and b.flags.c_contiguous and np.array_equal(b.reshape(4, 3), np.asarray(bad))
+    with pytest.raises(ValueError, match='expected 12 values'):
+        hb(a[:3], np.float64, 12, 'y0')
+    out = np.empty(4, dtype=np.int32)
+    assert hb(out, np.int32, 4, 'fetch', writable=True) is out
+    for bad in (np.empty(4, dtype=np.int64), np.empty(5, dtype=np.int32), np.empty(8, dtype=np.int32)[::2], [0, 0, 0, 0]):
+        with pytest.raises(ValueError, match='writable C-contiguous'):
+            hb(bad, np.int32, 4, 'fetch', writable=True)
+    torch = pytest.importorskip('torch')
+    t = torch.zeros(4, 3, dtype=torch.float64)
+    assert hb(t, np.float64, 12, 'y0') is t
+    for bad in (t.float(), t.t(), t[:3]):
+        with pytest.raises(ValueError, match='contiguous CPU tensor'):
+            hb(bad, np.float64, 12, 'y0')

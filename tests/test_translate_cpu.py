@@ -107,6 +107,53 @@ def test_unsupported_constructs_are_named():
         ni.translate(f_lorenz, 3, None, True)
 
 
+def f_runtime_float_rebound(t, y):
+    a = 2.0
+    if t > 1.0:
+        a = 3.0
+        k = 2  # a translate-time constant first bound under the condition: usable inside the branch only
+        a = a + k
+    return a * y
+
+
+def test_constants_and_returns_under_a_runtime_condition(tmp_path):
+    """an int-valued local rebound inside a run-time `if` was folded unconditionally, and a `return`
+    inside one was hoisted out of it.  Both are refused by name; the float form is a real variable."""
+    def int_rebound(t, y):
+        a = 2
+        if t > 1.0:
+            a = 3
+        return a * y
+
+    def tuple_rebound(t, y):
+        c = (1.0, 2.0)
+        if y[0] > 0.0:
+            c = (3.0, 4.0)
+        return np.array((c[0] * y[0], c[1] * y[1]))
+
+    def conditional_return(t, y):
+        if t > 1.0:
+            return 2.0 * y
+        return y
+
+    def scoped_constant_escapes(t, y):
+        if t > 1.0:
+            k = 2
+        return k * y
+    with pytest.raises(ni.TranslationError, match='reassigned inside a run-time `if`'):
+        ni.translate(int_rebound, 2)
+    with pytest.raises(ni.TranslationError, match='`return` inside a run-time `if`'):
+        ni.translate(conditional_return, 2)
+    with pytest.raises(ni.TranslationError):
+        ni.translate(scoped_constant_escapes, 2)
+    for k, fun in enumerate((f_runtime_float_rebound, tuple_rebound)):  # variables of the generated code: fine
+        body, P, Q, _ = ni.translate(fun, 2)
+        call = _compile(body, 2, P, Q, tmp_path, f'rt_{k}')
+        for t in (0.5, 1.5):
+            for y in (np.array((0.25, -3.0)), np.array((-0.25, 3.0))):
+                assert np.array_equal(call(t, y, np.zeros(0))[0], fun(t, y))
+
+
 def condition_exponential(solver, parameters):  # tests/unittests/test_public.py:145-147 of the reference
     return solver.y[0] > parameters
 

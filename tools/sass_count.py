@@ -1,10 +1,13 @@
-"""Static instruction counts of the run kernels' hot loops, read off the SASS with cuobjdump.
+"""Static instruction and register-operand counts of the run kernels' hot loops, read off the SASS with cuobjdump.
 
-The thread-per-trajectory run kernel is bound by issue slots: one attempt costs about 2 D + I scheduler cycles, D =
-FP64-pipe instructions, I = all others (profiles/r01_ablation_issue_model.txt).  This script
-prints D and I of one pass through the hot loop -- everything between the loop's EXIT test and its back edge, minus the
-cold regions (forward-skipped spans that contain a CALL: the operator slow paths) -- for every loop body of a kernel
-(ni_small_run_body carries two: max_step = inf and the general one).
+The thread-per-trajectory run kernel is bound by register-file read bandwidth (DESIGN.md section 3.2,
+profiles/r02_issue_model.txt: a scheduler reads two 32-bit register operands per lane per cycle, and an FP64 instruction
+with two 64-bit register sources uses that for both of its pipe cycles).  This script prints, for one pass through the
+hot loop -- everything between the loop's EXIT test and its back edge, minus the cold regions (forward-skipped spans that
+contain a CALL: the operator slow paths, the lean body's cold block) -- D = FP64-pipe instructions, I = all others, and
+R = 32-bit register source operands read (64-bit operands count twice, operands served by the reuse cache not at all):
+one attempt costs about max(2 D, R / 2) scheduler cycles.  Every loop body of a kernel is listed (ni_small_run_body
+carries two: the lean one and the general one).
 
     python tools/sass_count.py [object [mangled kernel name]]
 """
@@ -38,8 +41,41 @@ def _opcode(text):
     return re.sub(r'^@!?U?P\d\s+', '', text).split()[0].split('.')[0]
 
 
+def register_reads(body):
+    """32-bit register source operands of a list of (address, text) instructions; reuse-cache hits excluded."""
+    total = 0
+    prev_reuse = set()
+    for _, t in body:
+        tt = re.sub(r'^@!?U?P\d\s+', '', t)
+        head = tt.split()[0]
+        op = head.split('.')[0]
+        parts = [x.strip() for x in tt.split(None, 1)[1].split(',')] if ' ' in tt else []
+        if op in ('BRA', 'BSSY', 'BSYNC', 'EXIT', 'NOP', 'WARPSYNC', 'LDCU', 'LDC', 'S2R', 'CS2R', 'BREAK'):
+            srcs = []
+        elif op in ('STG', 'STL', 'STS', 'RED', 'REDG'):
+            srcs = parts
+        elif op in ('ISETP', 'DSETP', 'FSETP'):
+            srcs = parts[2:]
+        else:
+            srcs = parts[1:]
+        wide = op in FP64 or '.64' in head or op == 'DSETP'
+        cur_reuse = set()
+        for k, src in enumerate(srcs):
+            m = re.match(r'[-|~!]*(R\d+)(\.reuse)?', src)
+            if not m:
+                continue
+            w = 2 if wide else 1
+            if (k, m.group(1)) not in prev_reuse:
+                total += w
+            if m.group(2):
+                cur_reuse.add((k, m.group(1)))
+        prev_reuse = cur_reuse
+    return total
+
+
 def hot_loops(obj, kernel):
-    """[(histogram, n_fp64, n_other)] for every attempt loop of the kernel, in address order."""
+    """[(histogram, n_fp64, n_other)] for every attempt loop of the kernel, in address order; the histogram carries
+    the register-read count under the key '_reads'."""
     ins = disassemble(obj, kernel)
     loops = []
     for addr, text in ins:
@@ -61,9 +97,12 @@ def hot_loops(obj, kernel):
                 skipped = [b for b, u in body if a < b < int(mm.group(1), 16)]
                 if any('CALL' in u for b, u in body if b in skipped):
                     cold.update(skipped)
-        hist = collections.Counter(_opcode(t) for a, t in body if a not in cold)
+        hot = [(a, t) for a, t in body if a not in cold]
+        hist = collections.Counter(_opcode(t) for a, t in hot)
         d = sum(hist[k] for k in FP64)
-        loops.append((hist, d, sum(hist.values()) - d))
+        i = sum(hist.values()) - d
+        hist['_reads'] = register_reads(hot)
+        loops.append((hist, d, i))
     return loops
 
 
@@ -73,7 +112,9 @@ def main(argv):
         path = Path(obj) if Path(obj).exists() else BUILD / obj
         for hist, d, i in hot_loops(path, kernel):
             local = hist['STL'] + hist['LDL']
-            print(f'{label:28s} D = {d:4d}  I = {i:4d}  2D+I = {2 * d + i:4d}  local-memory accesses {local}')
+            r = hist.pop('_reads')
+            print(f'{label:28s} D = {d:4d}  I = {i:4d}  R = {r:4d}  max(2D, R/2) = {max(2 * d, r / 2):6.1f}  '
+                  f'local-memory accesses {local}')
             print('    ' + ' '.join(f'{k}:{v}' for k, v in hist.most_common()))
 
 
