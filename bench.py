@@ -7,7 +7,10 @@ One "step" integrates the whole ensemble shard of this GPU from t0 to t_bound: t
 persistent fast-forward kernel.  `value` is the whole-job aggregate (all ranks' accepted steps /
 max-over-ranks device time); `e2e` repeats the measurement through the C ABI with pinned HOST
 buffers (upload -> reset -> run -> download of terminal t, y, aux, counters) inside the timed
-region.  Weak scaling: every rank integrates its own --traj trajectories.
+region.  Weak scaling: every rank integrates its own --traj trajectories (`value`).  With more than one GPU the
+line also carries the one collective of the path -- the final NCCL gather of terminal records -- as
+`final_gather_ms` / `value_incl_gather`, and a `strong` record: the SAME --traj trajectories IN TOTAL sharded over
+the GPUs (the north-star configuration: 10 M Lorenz trajectories on 8 GPUs), gather included.
 
 The CPU oracle (oracle/) is used only as the reported baseline (`cpu_baseline`, `--impl reference`)
 -- never on the measured GPU path.
@@ -177,6 +180,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-fast', action='store_true', help='skip the extra fast-arithmetic launches (roofline.fast)')
     ap.add_argument('--arithmetic', default='strict', choices=['strict', 'fast'],
                     help="'strict' = the reference's unfused FP64 arithmetic (default, bit-faithful); 'fast' = opt-in mode")
     args = ap.parse_args()
@@ -209,18 +213,56 @@ def main():
     w = make_workload(args.workload, args.traj, rank, world, args.t_bound)
     N, n = w.N, w.n
     f = ni.BuiltinRHS(w.rhs)
-    ctor_kw = dict(rtol=w.rtol, atol=w.atol, device=local, arithmetic=args.arithmetic)
     record = args.workload == 'c2'
-    def build_ensemble():
-        if w.advanced:
-            Solver = ni.Advanced(f.P, f.Q, ni.RK45 if w.method == 'RK45' else ni.RK23)
-            e = Solver(f, w.t0, w.y0, w.params, w.t_bound, **ctor_kw)
+
+    def build_ensemble(wk=None, arithmetic=None):
+        wk = wk or w
+        kw = dict(rtol=wk.rtol, atol=wk.atol, device=local, arithmetic=arithmetic or args.arithmetic)
+        if wk.advanced:
+            Solver = ni.Advanced(f.P, f.Q, ni.RK45 if wk.method == 'RK45' else ni.RK23)
+            e = Solver(f, wk.t0, wk.y0, wk.params, wk.t_bound, **kw)
         else:
-            ctor = ni.RK45 if w.method == 'RK45' else ni.RK23
-            e = ctor(f(*w.params.T) if f.P else f, w.t0, w.y0, w.t_bound, **ctor_kw)
+            ctor = ni.RK45 if wk.method == 'RK45' else ni.RK23
+            e = ctor(f(*wk.params.T) if f.P else f, wk.t0, wk.y0, wk.t_bound, **kw)
         if record:
-            e.record_enable(int(N * 1000))  # the whole ensemble's accepted steps stay in HBM (~877 per trajectory)
+            e.record_enable(int(wk.N * 1000))  # the whole ensemble's accepted steps stay in HBM (~877 per trajectory)
         return e
+
+    def timed_steps(e, steps, warmup):
+        """`steps` x (init kernel + run kernel) on resident inputs: (total ms, mean run-kernel ms, accepted, attempts)."""
+        for _ in range(warmup):
+            e.reset()
+            e.run_async()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        a0.record()
+        for i in range(steps):
+            e.reset()
+            kv[i][0].record()
+            e.run_async()
+            kv[i][1].record()
+        a1.record()
+        barrier()
+        acc_ = e.n_accepted.astype(np.int64)
+        rej_ = e.n_rejected.astype(np.int64)
+        st = e.status
+        assert np.all(st == _lib.ST_FINISHED), f'{np.sum(st != _lib.ST_FINISHED)} trajectories did not finish'
+        return (a0.elapsed_time(a1), float(np.mean([x.elapsed_time(y) for x, y in kv])), int(acc_.sum()),
+                int(acc_.sum() + rej_.sum()))
+
+    def reduce_max(x):
+        tt = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def reduce_sum(*xs):
+        tt = torch.tensor(xs, dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return [float(v) for v in tt.tolist()]
 
     ens = build_ensemble()
     stream = torch.cuda.current_stream()
@@ -236,62 +278,66 @@ def main():
     except OSError:
         pass
 
-    def one_step():
-        ens.reset()
-        ens.run_async()
-
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
     launches0 = ens.timing()['launches']
     sampler = ClockSampler(local)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        ens.reset()
-        kev[i][0].record()
-        ens.run_async()
-        kev[i][1].record()
-    ev1.record()
-    barrier()
+    ms, run_ms, acc_rank, att_rank = timed_steps(ens, args.steps, args.warmup)
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    run_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    launches = ens.timing()['launches'] - launches0
-    acc = ens.n_accepted.astype(np.int64)
-    rej = ens.n_rejected.astype(np.int64)
-    status = ens.status
-    assert np.all(status == _lib.ST_FINISHED), f'{np.sum(status != _lib.ST_FINISHED)} trajectories did not finish'
-    acc_rank, att_rank = int(acc.sum()), int(acc.sum() + rej.sum())
-
-    tms = torch.tensor([ms], dtype=torch.float64, device='cuda')
-    tot = torch.tensor([acc_rank, att_rank], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max = float(tms.item())
-    acc_all = float(tot[0].item())
+    launches = ens.timing()['launches'] - launches0 - 2 * args.warmup
+    ms_max = reduce_max(ms)
+    acc_all, = reduce_sum(acc_rank)
     value = acc_all * args.steps / (ms_max * 1e-3)
 
-    # ---- the one collective of the path: final NCCL gather of terminal states + statistics (device buffers)
-    gather_ms = None
-    if world > 1:
+    # ---- the one collective of the path: final NCCL gather of terminal records (t, y, aux, counters, status)
+    def timed_gather(e, n_global, interleaved):
         from numba_integrators_b200 import distributed as nd
-        tens, small = nd.device_tensors(ens)
-        local = {k: (v.t().contiguous() if small and v.dim() == 2 else v) for k, v in tens.items()}
-        nd.all_gather_arrays(local)  # warm-up (NCCL channel setup)
+        g = nd.TerminalGather(e, n_global, interleaved)
+        g.run()  # warm-up (NCCL channel setup, buffer registration)
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        nd.all_gather_arrays(local)
-        g1.record()
-        barrier()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device='cuda')
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather_ms = float(gt.item())
+        best = None
+        for _ in range(3):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            g0.record()
+            g.run()
+            g1.record()
+            barrier()
+            tmax = reduce_max(g0.elapsed_time(g1))
+            best = tmax if best is None else min(best, tmax)
+        return best, g.dtype.itemsize
+
+    gather_ms, strong = None, None
+    if world > 1:
+        gather_ms, rec_bytes = timed_gather(ens, N * world, False)
+        # ---- strong scaling: the single-GPU problem (--traj trajectories IN TOTAL) sharded over the GPUs
+        from numba_integrators_b200 import distributed as nd
+        from numba_integrators_b200.workloads import Workload
+        wg = make_workload(args.workload, args.traj, 0, 1, args.t_bound)
+        inter = args.workload == 'c4'  # sorted parameter sweep: interleave so that every GPU gets the same cost
+        idx = nd.shard_indices(wg.N, rank, world, inter)
+        ws = Workload(wg.name, wg.rhs, wg.method, wg.advanced, wg.t0, wg.t_bound, np.ascontiguousarray(wg.y0[idx]),
+                      None if wg.params is None else np.ascontiguousarray(wg.params[idx]), wg.rtol, wg.atol,
+                      wg.flops_per_attempt, wg.record_bytes_per_step)
+        del wg
+        ens_s = build_ensemble(ws)
+        ens_s.set_stream(stream.cuda_stream)
+        s_ms, s_run, s_acc, s_att = timed_steps(ens_s, args.steps, args.warmup)
+        s_ms_max = reduce_max(s_ms)
+        s_run_max = reduce_max(s_run)
+        s_acc_all, s_att_all = reduce_sum(s_acc, s_att)
+        s_gather, _ = timed_gather(ens_s, args.traj, inter)
+        step_ms = s_ms_max / args.steps
+        strong = {'trajectories_total': args.traj, 'trajectories_per_gpu': len(idx), 'ms_per_step': step_ms,
+                  'value': s_acc_all / (step_ms * 1e-3), 'final_gather_ms': s_gather,
+                  'ms_incl_gather': step_ms + s_gather, 'value_incl_gather': s_acc_all / ((step_ms + s_gather) * 1e-3),
+                  'run_kernel_ms_max_over_ranks': s_run_max,
+                  'gather_GBps_per_rank': rec_bytes * args.traj * (world - 1) / world / (s_gather * 1e-3) / 1e9,
+                  'efficiency_vs_weak_per_gpu_rate': (s_acc_all / (step_ms * 1e-3)) / value,
+                  'efficiency_vs_weak_incl_gather': (s_acc_all / ((step_ms + s_gather) * 1e-3)) / value,
+                  'note': 'the same trajectories a 1-GPU run integrates, sharded by index; efficiency = strong rate / '
+                          '(weak whole-job rate, i.e. n_gpus x the per-GPU rate at full occupancy)'}
+        strong['_fp64_flops'] = ws.flops_per_attempt * s_att_all  # -> frac below, once the peak is known
+        del ens_s
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
@@ -299,23 +345,17 @@ def main():
         P, Q = ens.P, ens.Q
         y0_h = torch.from_numpy(w.y0).pin_memory()
         par_h = torch.from_numpy(w.params).pin_memory() if P else None
-        out = {
-            _lib.F_T: torch.empty(N, dtype=torch.float64).pin_memory(),
-            _lib.F_Y: torch.empty((N, n), dtype=torch.float64).pin_memory(),
-            _lib.F_N_ACCEPTED: torch.empty(N, dtype=torch.int32).pin_memory(),
-            _lib.F_N_REJECTED: torch.empty(N, dtype=torch.int32).pin_memory(),
-            _lib.F_STATUS: torch.empty(N, dtype=torch.int32).pin_memory(),
-        }
-        if Q:
-            out[_lib.F_AUX] = torch.empty((N, Q), dtype=torch.float64).pin_memory()
+        # the step's result: ONE packed terminal record per trajectory (t, y, aux, n_accepted, n_rejected, status)
+        rec_dt = ens.terminal_dtype()
+        out = torch.empty(N * rec_dt.itemsize, dtype=torch.uint8).pin_memory()
         h2d = y0_h.numel() * 8 + (par_h.numel() * 8 if P else 0) + 16
-        d2h = sum(t.numel() * t.element_size() for t in out.values())
+        d2h = out.numel()
 
         # Two ensembles on two streams (double buffering): while one integrates, the other one's inputs are
         # uploaded and the previous results are downloaded.  Every step still uploads its own inputs and downloads
         # its own results inside the timed region.
         ens_b = build_ensemble()
-        out_b = {k: torch.empty_like(v).pin_memory() for k, v in out.items()}
+        out_b = torch.empty_like(out).pin_memory()
         s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
         ens.set_stream(s_a.cuda_stream)
         ens_b.set_stream(s_b.cuda_stream)
@@ -329,8 +369,7 @@ def main():
 
         def collect(i):
             e, o = lanes[i % 2]
-            for fld, buf in o.items():
-                e.fetch(fld, buf)
+            e.fetch_terminal(o)  # pack kernel + one device-to-host copy + stream synchronise
 
         launch(0)
         launch(1)
@@ -351,12 +390,31 @@ def main():
         if world > 1:
             dist.all_reduce(tms2, op=dist.ReduceOp.MAX)
         for o in (out, out_b):
-            acc_e2e = int(o[_lib.F_N_ACCEPTED].numpy().astype(np.int64).sum())
-            assert acc_e2e == acc_rank, (acc_e2e, acc_rank)
+            rec = o.numpy().view(rec_dt)
+            acc_e2e = int(rec['n_accepted'].astype(np.int64).sum())
+            assert acc_e2e == acc_rank and np.all(rec['status'] == _lib.ST_FINISHED), (acc_e2e, acc_rank)
         e2e = {'value': acc_all * args.steps / (float(tms2.item()) * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': d2h, 'ms_per_step': float(tms2.item()) / args.steps,
-               'path': 'ni_ensemble_upload(pinned) -> ni_ensemble_reset -> ni_ensemble_run_async -> ni_ensemble_get x%d, '
-                       'two ensembles double-buffered on two CUDA streams' % len(out)}
+               'path': 'ni_ensemble_upload(pinned) -> ni_ensemble_reset -> ni_ensemble_run_async -> '
+                       'ni_ensemble_get_terminal (packed t, y, aux, counters, status: one copy), two ensembles '
+                       'double-buffered on two CUDA streams'}
+
+    # ---- the opt-in fast arithmetic on the same workload: one extra ensemble, three timed launches (rank 0's GPU)
+    fast = None
+    if args.arithmetic == 'strict' and not args.no_fast and not record:
+        ens.set_stream(stream.cuda_stream)
+        try:
+            ens_f = build_ensemble(arithmetic='fast')
+            ens_f.set_stream(stream.cuda_stream)
+            f_ms, f_run, f_acc, f_att = timed_steps(ens_f, 3, 2)
+            fast = {'value': f_acc * 3 / (f_ms * 1e-3), 'kernel_ms': f_run,
+                    'achieved': w.flops_per_attempt * f_att / (f_run * 1e-3) / 1e12,
+                    'note': "arithmetic='fast' (contracted multiply-adds, MUFU-seeded reciprocal and controller root): "
+                            'meets the 1e-12 / identical-counts bar, not bit-faithful; this GPU only, 3 launches'}
+            fast['frac'] = fast['achieved'] / fp64_peak if fp64_peak else None
+            del ens_f
+        except ni.NiError as exc:  # no fast variant for this kernel family
+            fast = {'unavailable': str(exc)}
 
     if rank == 0:
         flops = w.flops_per_attempt * att_rank  # algorithmic flops of one launch
@@ -366,12 +424,13 @@ def main():
                     'frac': achieved / fp64_peak if fp64_peak else None, 'traffic': None,
                     'kernel': kname, 'kernel_ms': run_ms,
                     'flops_per_attempt': w.flops_per_attempt, 'attempts_per_launch': att_rank,
-                    'peak_source': 'live DFMA-chain microbenchmark ni_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; '
-                                   'nominal 37.2 TFLOP/s)',
+                    'peak_source': 'live DFMA-chain microbenchmark ni_fp64_peak, operand form DFMA R,R,R,UR (MEASURED_PEAKS.json '
+                                   'has no FP64 entry; nominal 37.2 TFLOP/s; ncu of the same kernel: FP64 pipe 99.97 % busy, '
+                                   'profiles/r02_fp64_peak_kernel_ncu.csv)',
                     'hbm_gbs_measured': peaks.get('hbm_gbs')}
         try:  # DRAM traffic of this kernel measured by ncu (profiles/), scaled to this launch's trajectory count
             key = args.workload + ('_fast' if args.arithmetic == 'fast' else '')
-            tr = json.loads((ROOT / 'profiles' / 'r01_dram_traffic.json').read_text()).get(key)
+            tr = json.loads((ROOT / 'profiles' / 'r02_dram_traffic.json').read_text()).get(key)
             if tr:
                 roofline['traffic'] = tr['bytes_per_trajectory'] * N
                 roofline['traffic_source'] = tr['capture']
@@ -408,8 +467,20 @@ def main():
                            'l2': f'inputs {N * (n + ens.P) * 8 / 1e6:.0f} MB + state per launch exceed the 126 MB L2',
                            'accepted_per_traj': acc_rank / N, 'rejected_per_traj': (att_rank - acc_rank) / N},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline}
+        if fast is not None:
+            roofline['fast'] = fast
         if gather_ms is not None:
-            line['final_gather_ms'] = gather_ms  # NCCL all_gather of t, y, aux, counters, status (not in a step)
+            # the one collective of the path, once per job after the last step: pack kernel + ONE NCCL
+            # all_gather_into_tensor of equal-sized record slots (not part of `value`, which is the driver's weak-scaling
+            # figure; `value_incl_gather` charges it to every step)
+            step_ms = ms_max / args.steps
+            line['final_gather_ms'] = gather_ms
+            line['ms_incl_gather'] = step_ms + gather_ms
+            line['value_incl_gather'] = acc_all / ((step_ms + gather_ms) * 1e-3)
+            line['gather_GBps_per_rank'] = rec_bytes * N * (world - 1) / (gather_ms * 1e-3) / 1e9
+        if strong is not None:
+            strong['frac'] = strong.pop('_fp64_flops') / world / (strong['run_kernel_ms_max_over_ranks'] * 1e-3) / 1e12 / fp64_peak
+            line['strong'] = strong
         if world == 1 and not args.no_cpu_baseline:
             rate, k, threads, dt = cpu_oracle_rate(w, args.cpu_seconds)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',

@@ -171,6 +171,19 @@ int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in); /* NI_F_T_B
 int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr);  /* zero-copy view (NCCL gather) */
 int ni_ensemble_set_max_attempts(ni_ensemble *e, int64_t per_launch);
 
+/* ---- terminal records: the payload of the final multi-GPU gather ------------------------
+ * after the integration the only cross-GPU traffic is the gather of terminal
+ * t, y, auxiliary and the step statistics (the reference has no counterpart: one jitclass object = one trajectory,
+ * _basic.py:182-199 lists the same fields).  ni_ensemble_pack_terminal writes ONE packed row per trajectory,
+ *   double t, y[n], aux[Q]; int32 n_accepted, n_rejected, status        (8 (1 + n + Q) + 12 bytes, 4-byte aligned)
+ * into a caller-owned DEVICE buffer of N rows, asynchronously on the ensemble's stream, so that a caller holding a
+ * communicator moves every shard with a single all-gather / gather of equal-sized rows
+ * (numba_integrators_b200/distributed.py does it with torch.distributed over NCCL; the library itself carries no
+ * communicator: one process drives one GPU).  ni_ensemble_get_terminal = pack + one device-to-host copy + sync. */
+int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory);
+int ni_ensemble_pack_terminal(ni_ensemble *e, void *dst_device);
+int ni_ensemble_get_terminal(ni_ensemble *e, void *host_out);
+
 
 /* ---- recording of accepted steps into an HBM append log --------------------------------
  * (README.md:62-69 appends solver.t / solver.y after every accepted step.)  Records are

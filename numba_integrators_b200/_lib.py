@@ -56,6 +56,9 @@ SIGNATURES = {
     'ni_ensemble_set': (C.c_int, [_vp, C.c_int, _vp]),
     'ni_ensemble_device_ptr': (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     'ni_ensemble_set_max_attempts': (C.c_int, [_vp, C.c_int64]),
+    'ni_ensemble_terminal_bytes': (C.c_int, [_vp, _i64p]),
+    'ni_ensemble_pack_terminal': (C.c_int, [_vp, _vp]),
+    'ni_ensemble_get_terminal': (C.c_int, [_vp, _vp]),
     'ni_ensemble_record_enable': (C.c_int, [_vp, C.c_int64]),
     'ni_ensemble_record_count': (C.c_int, [_vp, _i64p]),
     'ni_ensemble_record_drain': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i64p]),

@@ -352,6 +352,28 @@ class Ensemble:
         check(self._L.ni_ensemble_get(self._h, field, _ptr(buf)))
         return out
 
+    # ------------------------------------------------------------------ terminal records (final gather)
+    def terminal_dtype(self):
+        """numpy dtype of one packed terminal record (ni_ensemble_pack_terminal): t, y, aux, counters, status."""
+        return terminal_dtype(self.n, self.Q)
+
+    def pack_terminal(self, dst_device_ptr):
+        """Asynchronously pack N terminal records into a caller-owned device buffer (N * terminal_dtype().itemsize B)."""
+        check(self._L.ni_ensemble_pack_terminal(self._h, _lib._vp(int(dst_device_ptr))))
+
+    def fetch_terminal(self, out):
+        """Pack + one device-to-host copy of the N terminal records into a caller-owned byte buffer (numpy uint8 array
+        or pinned torch tensor of N * terminal_dtype().itemsize bytes)."""
+        buf = _host_buffer(out, np.uint8, self.N * self.terminal_dtype().itemsize, 'fetch_terminal', writable=True)
+        check(self._L.ni_ensemble_get_terminal(self._h, _ptr(buf)))
+        return out
+
+    def terminal(self):
+        """The terminal records on the host: structured array (t, y, aux, n_accepted, n_rejected, status), one D2H copy."""
+        out = np.empty(self.N, dtype=self.terminal_dtype())
+        check(self._L.ni_ensemble_get_terminal(self._h, out.ctypes.data))
+        return out
+
     # ------------------------------------------------------------------ recording
     def record_enable(self, capacity):
         check(self._L.ni_ensemble_record_enable(self._h, int(capacity)))
@@ -402,6 +424,15 @@ class Ensemble:
         a, b, c = C.c_float(0), C.c_float(0), C.c_int64(0)
         check(self._L.ni_ensemble_timing(self._h, a, b, c))
         return dict(ms_init=a.value, ms_run=b.value, launches=c.value)
+
+
+def terminal_dtype(n, Q):
+    """Packed terminal record of include/ni_b200.h: double t, y[n], aux[Q]; int32 n_accepted, n_rejected, status."""
+    fields = [('t', '<f8'), ('y', '<f8', (n,))] + ([('aux', '<f8', (Q,))] if Q else []) + \
+             [('n_accepted', '<i4'), ('n_rejected', '<i4'), ('status', '<i4')]
+    dt = np.dtype(fields)
+    assert dt.itemsize == 8 * (1 + n + Q) + 12
+    return dt
 
 
 def _ptr(x):

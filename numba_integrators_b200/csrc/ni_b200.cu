@@ -920,6 +920,35 @@ __global__ void ni_k_rec_rows(const double *src, double *dst, long long count, l
   }
 }
 
+// ---- terminal records (the final gather moves terminal t, y, aux and the step statistics)
+// One packed row per trajectory: double t, y[n], aux[Q]; int32 n_accepted, n_rejected, status -- 8 (1 + n + Q) + 12
+// bytes (52 for Lorenz-63 via Advanced).  One thread per 32-bit word of the output, so the stores are coalesced; the
+// loads hit the row-major mirror of y (small kernels) or the trajectory-major state (large kernels).
+__global__ void ni_k_pack_terminal(NiArgs a, int small, int n, int Q, unsigned *dst) {
+  const int dwords = 2 * (1 + n + Q), W = dwords + 3;
+  const long long total = a.N * W;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long i = g / W;
+    const int w = (int)(g - i * W);
+    unsigned out;
+    if (w < dwords) {
+      const int d = w >> 1;
+      double v;
+      if (d == 0)
+        v = a.t[i];
+      else if (d <= n)
+        v = small ? (a.y_rows ? a.y_rows[i * n + (d - 1)] : a.y[(long long)(d - 1) * a.N + i]) : a.y[i * n + (d - 1)];
+      else
+        v = small ? a.aux[(long long)(d - 1 - n) * a.N + i] : a.aux[i * Q + (d - 1 - n)];
+      out = (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
+    } else {
+      const int k = w - dwords;
+      out = (unsigned)(k == 0 ? a.n_acc[i] : k == 1 ? a.n_rej[i] : a.status[i]);
+    }
+    dst[g] = out;
+  }
+}
+
 static int grid_for(long long work) {
   long long g = (work + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -1109,6 +1138,38 @@ NI_API int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in) {
   } else {
     return fail(NI_ERR_INVALID, "field %d is read-only", field);
   }
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
+// ---- terminal records for the final gather
+NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory) {
+  if (!e || !bytes_per_trajectory) return fail(NI_ERR_INVALID, "ensemble / bytes_per_trajectory is NULL");
+  *bytes_per_trajectory = 8ll * (1 + e->mod.n + e->mod.Q) + 12;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_pack_terminal(ni_ensemble *e, void *dst_device) {
+  if (!e || !dst_device) return fail(NI_ERR_INVALID, "ensemble / dst_device is NULL");
+  if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
+  CU(cudaSetDevice(e->device));
+  const long long words = (long long)e->N * (2 * (1 + e->mod.n + e->mod.Q) + 3);
+  ni_k_pack_terminal<<<grid_for(words), 256, 0, e->stream>>>(e->a, e->mod.kind == NI_KIND_SMALL ? 1 : 0, e->mod.n, e->mod.Q,
+                                                             (unsigned *)dst_device);
+  CU(cudaGetLastError());
+  e->n_launches++;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_get_terminal(ni_ensemble *e, void *host_out) {
+  if (!e || !host_out) return fail(NI_ERR_INVALID, "ensemble / host_out is NULL");
+  int64_t rb = 0;
+  ni_ensemble_terminal_bytes(e, &rb);
+  const size_t bytes = (size_t)e->N * (size_t)rb;
+  CU(cudaSetDevice(e->device));
+  if (int rc = need_scratch(e, bytes)) return rc;
+  if (int rc = ni_ensemble_pack_terminal(e, e->scratch)) return rc;
+  CU(cudaMemcpyAsync(host_out, e->scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   return NI_OK;
 }

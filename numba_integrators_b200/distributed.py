@@ -1,9 +1,9 @@
 """Multi-GPU plumbing: one process per GPU (torchrun), trajectories sharded by index.
 
 The integration itself needs no communication -- trajectories are independent.
-The only collective is the final gather of terminal states and statistics, done with
-`torch.distributed.all_gather` (NCCL over NVLink on GPUs; gloo in the CPU tests) directly on the
-ensemble's device buffers (zero-copy views through __cuda_array_interface__).
+The only collective is the final gather of terminal states and statistics: one packed record per
+trajectory (`ni_ensemble_pack_terminal`), one `all_gather_into_tensor` of equal-sized slots over NCCL
+(NVLink / NVSwitch); the CPU tests run the same record layout and merge logic over gloo.
 """
 from __future__ import annotations
 
@@ -67,27 +67,85 @@ def device_tensors(ens):
     return out, small
 
 
-def all_gather_arrays(local: dict, group=None):
-    """all_gather a dict of equally-shaped-per-rank tensors/arrays; returns {name: [rank0, rank1, ...]}.
-    Shards may have different lengths along axis 0 (padded to the maximum for the collective)."""
+def shard_rows(N, world):
+    """Rows of the gather buffer per rank: the largest shard (equal-sized slots, no size exchange: every rank
+    derives every shard's length from N and the sharding rule)."""
+    return (N + world - 1) // world
+
+
+class TerminalGather:
+    """The one collective of the path: terminal records of every shard to every rank (or to rank 0).
+
+    Each rank packs its N_r trajectories into rows of `terminal_dtype` (t, y, aux, n_accepted, n_rejected, status:
+    52 bytes for Lorenz-63) with ONE kernel (ni_ensemble_pack_terminal) straight into its slot of a preallocated
+    (world, rows, record) buffer; ONE `all_gather_into_tensor` (or `gather` to rank 0) moves them; shard lengths come
+    from `shard_indices`, so there is no size exchange, no host synchronisation and no per-field collective.
+    Buffers are allocated once and reused by every `run()`."""
+
+    def __init__(self, ens, N_global, interleaved=False, group=None, to_rank0=False):
+        import torch
+        import torch.distributed as dist
+        self.ens, self.N, self.interleaved, self.group, self.to_rank0 = ens, int(N_global), interleaved, group, to_rank0
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dtype = ens.terminal_dtype()
+        self.rows = shard_rows(self.N, self.world)
+        own = len(shard_indices(self.N, self.rank, self.world, interleaved))
+        if own != ens.N:
+            raise ValueError(f'rank {self.rank} holds {ens.N} trajectories, the sharding rule gives it {own} of {self.N}')
+        dev = torch.device('cuda', ens.device)
+        nbytes = self.rows * self.dtype.itemsize
+        # own slot is part of the receive buffer: the pack kernel writes where the collective reads (in place)
+        self.recv = torch.zeros((self.world, nbytes), dtype=torch.uint8, device=dev)
+        self.send = self.recv[self.rank]
+
+    def run(self):
+        """Pack + collective, asynchronous on the ensemble's stream / NCCL's stream; returns the device buffer
+        (world, rows * record bytes) -- on every rank, or meaningful on rank 0 only with `to_rank0`."""
+        import torch.distributed as dist
+        self.ens.pack_terminal(self.send.data_ptr())
+        if self.to_rank0:
+            dist.gather(self.send, list(self.recv.unbind(0)) if self.rank == 0 else None, dst=0, group=self.group)
+        else:
+            dist.all_gather_into_tensor(self.recv.view(-1), self.send, group=self.group)
+        return self.recv
+
+    def host(self):
+        """The gathered records as numpy arrays in GLOBAL trajectory order (one D2H copy)."""
+        recs = self.recv.cpu().numpy().view(self.dtype).reshape(self.world, self.rows)
+        return merge_records(recs, self.N, self.world, self.interleaved)
+
+
+def merge_records(recs, N, world, interleaved=False):
+    """(world, rows) structured terminal records -> dict of (N, ...) arrays in global trajectory order."""
+    out = None
+    for r in range(world):
+        idx = shard_indices(N, r, world, interleaved)
+        part = recs[r, :len(idx)]
+        if out is None:
+            out = {name: np.empty((N,) + part[name].shape[1:], dtype=part[name].dtype) for name in part.dtype.names}
+        for name in part.dtype.names:
+            out[name][idx] = part[name]
+    if 'aux' in out:
+        out['auxiliary'] = out.pop('aux')
+    return out
+
+
+def all_gather_records(local, N, group=None):
+    """Backend-neutral form of the same collective for host arrays (the gloo tests): `local` is this rank's
+    structured record array; returns the (world, rows) array of every rank's records."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = {}
-    for name, v in local.items():
-        tns = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
-        n0 = torch.tensor([tns.shape[0]], dtype=torch.int64, device=tns.device)
-        sizes = [torch.zeros_like(n0) for _ in range(world)]
-        dist.all_gather(sizes, n0, group=group)
-        sizes = [int(s.item()) for s in sizes]
-        m = max(sizes)
-        if tns.shape[0] < m:
-            pad = torch.zeros((m - tns.shape[0],) + tuple(tns.shape[1:]), dtype=tns.dtype, device=tns.device)
-            tns = torch.cat([tns, pad], dim=0)
-        bufs = [torch.empty_like(tns) for _ in range(world)]
-        dist.all_gather(bufs, tns.contiguous(), group=group)
-        out[name] = [b[:s] for b, s in zip(bufs, sizes)]
-    return out
+    rows = shard_rows(N, world)
+    send = np.zeros(rows, dtype=local.dtype)
+    send[:len(local)] = local
+    s = torch.from_numpy(send.view(np.uint8))
+    recv = torch.empty((world, s.numel()), dtype=torch.uint8)
+    try:
+        dist.all_gather_into_tensor(recv.view(-1), s, group=group)
+    except (RuntimeError, NotImplementedError):  # a backend without the flat form: same data through the list form
+        dist.all_gather(list(recv.unbind(0)), s, group=group)
+    return recv.numpy().view(local.dtype).reshape(world, rows)
 
 
 def merge_shards(parts, N, world, interleaved=False):
@@ -102,15 +160,17 @@ def merge_shards(parts, N, world, interleaved=False):
 def gather(ens, N_global=None, interleaved=False, group=None):
     """Final gather of terminal t, y, auxiliary and the step statistics of a sharded ensemble.
 
-    Every rank receives the full arrays in global trajectory order (numpy, host).  On GPUs the
-    collective runs on the ensemble's own device buffers over NCCL; one D2H copy follows."""
+    Every rank receives the full arrays in global trajectory order (numpy, host): one pack kernel, one NCCL
+    all-gather of equal-sized record slots, one D2H copy."""
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    if N_global is None:  # the only case that needs an exchange: the caller did not say how many trajectories exist
+        n = torch.tensor([ens.N], dtype=torch.int64, device=torch.device('cuda', ens.device))
+        dist.all_reduce(n, group=group)
+        N_global = int(n.item())
+    g = TerminalGather(ens, N_global, interleaved, group)
     ens.sync()
-    tens, small = device_tensors(ens)
-    # trajectory axis first for the collective
-    local = {k: (v.t().contiguous() if small and v.dim() == 2 else v) for k, v in tens.items()}
-    got = all_gather_arrays(local, group)
-    sizes = [len(p) for p in got['t']]
-    N = N_global if N_global is not None else sum(sizes)
-    return {k: merge_shards([p.cpu().numpy() for p in parts], N, world, interleaved) for k, parts in got.items()}
+    g.run()
+    torch.cuda.synchronize()
+    return g.host()

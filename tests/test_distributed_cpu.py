@@ -28,20 +28,57 @@ def test_merge_is_inverse_of_shard():
         assert np.array_equal(nd.merge_shards(parts, 33, 4, inter), y)
 
 
+def _records(N, n, Q):
+    """Synthetic terminal records in the layout of ni_ensemble_pack_terminal (include/ni_b200.h)."""
+    from numba_integrators_b200._solver import terminal_dtype
+    rec = np.zeros(N, dtype=terminal_dtype(n, Q))
+    rec['t'] = np.arange(N) * 0.5
+    rec['y'] = np.arange(N * n, dtype=np.float64).reshape(N, n)
+    if Q:
+        rec['aux'] = -np.arange(N * Q, dtype=np.float64).reshape(N, Q)
+    rec['n_accepted'] = np.arange(N) * 7
+    rec['n_rejected'] = np.arange(N) % 5
+    rec['status'] = 1
+    return rec
+
+
+def test_terminal_record_layout():
+    from numba_integrators_b200._solver import terminal_dtype
+    dt = terminal_dtype(3, 1)  # Lorenz-63 through Advanced: the 52-byte record of SURVEY.md section 8e
+    assert dt.itemsize == 52 and dt.names == ('t', 'y', 'aux', 'n_accepted', 'n_rejected', 'status')
+    assert [dt.fields[k][1] for k in dt.names] == [0, 8, 32, 40, 44, 48]
+    assert terminal_dtype(2, 0).itemsize == 36 and 'aux' not in terminal_dtype(2, 0).names
+
+
+def test_merge_records_is_inverse_of_sharding():
+    N, world = 37, 4
+    rec = _records(N, 3, 1)
+    rows = nd.shard_rows(N, world)
+    for inter in (False, True):
+        slots = np.zeros((world, rows), dtype=rec.dtype)
+        for r in range(world):
+            idx = nd.shard_indices(N, r, world, inter)
+            slots[r, :len(idx)] = rec[idx]
+        full = nd.merge_records(slots, N, world, inter)
+        assert np.array_equal(full['y'], rec['y']) and np.array_equal(full['auxiliary'], rec['aux'])
+        assert np.array_equal(full['n_accepted'], rec['n_accepted']) and np.array_equal(full['t'], rec['t'])
+
+
 def _worker(rank, world, port, interleaved, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        N = 37                                     # ragged: shards of unequal length
-        y = np.arange(N * 3, dtype=np.float64).reshape(N, 3)
-        acc = np.arange(N, dtype=np.int32) * 7
-        mine, idx = nd.shard({'y': y, 'n_accepted': acc}, rank, world, interleaved)
-        got = nd.all_gather_arrays(mine)
-        full = {k: nd.merge_shards([p.numpy() for p in parts], N, world, interleaved) for k, parts in got.items()}
-        ok = np.array_equal(full['y'], y) and np.array_equal(full['n_accepted'], acc)
-        total = torch.tensor([float(mine['n_accepted'].sum())], dtype=torch.float64)
+        N = 37                                     # ragged: shards of unequal length, equal-sized slots
+        rec = _records(N, 3, 1)
+        idx = nd.shard_indices(N, rank, world, interleaved)
+        slots = nd.all_gather_records(rec[idx], N)  # ONE collective, no size exchange
+        full = nd.merge_records(slots, N, world, interleaved)
+        ok = all(np.array_equal(full[k], rec[s]) for k, s in (('t', 't'), ('y', 'y'), ('auxiliary', 'aux'),
+                                                             ('n_accepted', 'n_accepted'), ('n_rejected', 'n_rejected'),
+                                                             ('status', 'status')))
+        total = torch.tensor([float(rec['n_accepted'][idx].sum())], dtype=torch.float64)
         dist.all_reduce(total)                     # the bench's whole-job aggregate
-        ok = ok and total.item() == float(acc.sum())
+        ok = ok and total.item() == float(rec['n_accepted'].sum())
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

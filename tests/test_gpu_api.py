@@ -194,6 +194,30 @@ def test_device_views_and_nccl_gather_single_rank():
     assert np.array_equal(full_big['y'], big.y) and np.array_equal(full_big['n_accepted'], big.n_accepted)
     assert np.array_equal(full['y'], ens.y) and np.array_equal(full['t'], ens.t)
     assert np.array_equal(full['auxiliary'], ens.auxiliary) and np.array_equal(full['n_accepted'], ens.n_accepted)
+    assert np.array_equal(full['n_rejected'], ens.n_rejected) and np.array_equal(full['status'], ens.status)
+
+
+def test_terminal_records_equal_the_field_getters():
+    """ni_ensemble_pack_terminal / ni_ensemble_get_terminal: one packed row per trajectory (t, y, aux, counters,
+    status) for both device layouts -- the payload of the final gather, and a one-copy download."""
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c3_lorenz(N=777, t_bound=1.0)
+    ens = ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    ens.run()
+    h = wl.c5_heat(N=5, n=300, t_bound=1.0)
+    big = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 1.0, rtol=1e-8, atol=1e-8)
+    big.run()
+    v = wl.c4_vanderpol(N=333, t_bound=2.0)
+    vdp = ni.RK23(ni.rhs.vanderpol(v.params[:, 0]), 0.0, v.y0, 2.0, rtol=1e-6, atol=1e-6)
+    vdp.run()
+    for e in (ens, big, vdp):
+        rec = e.terminal()
+        assert rec.dtype.itemsize == 8 * (1 + e.n + e.Q) + 12 and rec.shape == (e.N,)
+        assert np.array_equal(rec['t'], e.t) and np.array_equal(rec['y'], e.y)
+        assert np.array_equal(rec['n_accepted'], e.n_accepted) and np.array_equal(rec['n_rejected'], e.n_rejected)
+        assert np.array_equal(rec['status'], e.status)
+        if e.Q:
+            assert np.array_equal(rec['aux'], e.auxiliary)
 
 
 def test_user_rhs_n8_coupled_oscillators_against_scipy_like_accuracy():
