@@ -56,6 +56,8 @@ SIGNATURES = {
     'ni_ensemble_set': (C.c_int, [_vp, C.c_int, _vp]),
     'ni_ensemble_device_ptr': (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     'ni_ensemble_set_max_attempts': (C.c_int, [_vp, C.c_int64]),
+    'ni_ensemble_compaction': (C.c_int, [_vp, C.c_int, _i64p]),
+    'ni_ensemble_set_step_limits': (C.c_int, [_vp, _vp, _vp]),
     'ni_ensemble_terminal_bytes': (C.c_int, [_vp, _i64p]),
     'ni_ensemble_pack_terminal': (C.c_int, [_vp, _vp]),
     'ni_ensemble_get_terminal': (C.c_int, [_vp, _vp]),

@@ -137,7 +137,15 @@ class Ensemble:
         order, self.n_stages, self.A, self.B, self.C, self.E = _TABLEAU[method]
         self.error_exponent = -1 / (order + 1)
         self.rtol, self.atol = rtol, atol
-        self.max_step = float(max_step)
+        # max_step / first_step: scalars as in the reference (_basic.py:292-299), or one value per trajectory
+        self._max_step_v = self._first_step_v = None
+        if np.ndim(max_step) > 0:
+            self._max_step_v = np.ascontiguousarray(np.broadcast_to(np.asarray(max_step, dtype=np.float64), (self.N,)))
+            max_step = np.inf if self.N != 1 else self._max_step_v[0]
+        if np.ndim(first_step) > 0:
+            self._first_step_v = np.ascontiguousarray(np.broadcast_to(np.asarray(first_step, dtype=np.float64), (self.N,)))
+            first_step = 0.0 if self.N != 1 else self._first_step_v[0]
+        self._max_step = float(max_step)
         self._first_step = float(first_step)
         t0a = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (self.N,)))
         tba = np.ascontiguousarray(np.broadcast_to(np.asarray(t_bound, dtype=np.float64), (self.N,)))
@@ -183,9 +191,13 @@ class Ensemble:
         self._h = h
         if record:
             self.record_enable(record)
+        if self._max_step_v is not None or self._first_step_v is not None:
+            check(self._L.ni_ensemble_set_step_limits(
+                self._h, None if self._max_step_v is None else self._max_step_v.ctypes.data,
+                None if self._first_step_v is None else self._first_step_v.ctypes.data))
         check(self._L.ni_ensemble_init(self._h, t0a.ctypes.data, 1, y0.ctypes.data,
                                        par.ctypes.data if par is not None else None, tba.ctypes.data, 1,
-                                       rtol.ctypes.data_as(_lib._dp), atol.ctypes.data_as(_lib._dp), self.max_step,
+                                       rtol.ctypes.data_as(_lib._dp), atol.ctypes.data_as(_lib._dp), self._max_step,
                                        self._first_step))
 
     # ------------------------------------------------------------------ lifetime
@@ -226,6 +238,13 @@ class Ensemble:
             a = a[:, 0]
         return self._scalar_or_array(a)
     step_size = property(lambda s: s._scalar_or_array(s._get(_lib.F_STEP_SIZE, None)))
+
+    @property
+    def max_step(self):  # _basic.py:188: a scalar field of the jitclass; one value per trajectory when given as an array
+        if self._max_step_v is not None:
+            return self._scalar_or_array(self._max_step_v.copy())
+        return self._max_step
+
     direction = property(lambda s: s._scalar_or_array(s._get(_lib.F_DIRECTION, None)))
     parameters = property(lambda s: s._scalar_or_array(s._get(_lib.F_PARAMS, s.P)))
     status = property(lambda s: s._scalar_or_array(s._get(_lib.F_STATUS, None, np.int32)))
@@ -235,7 +254,10 @@ class Ensemble:
     @property
     def nfev(self):
         """RHS evaluations: 1 (FSAL seed) + 1 (select_initial_step) + n_stages per attempt."""
-        n_init = 2 if self._first_step == 0.0 else 1
+        if self._first_step_v is not None:
+            n_init = self._scalar_or_array(np.where(self._first_step_v == 0.0, 2, 1))
+        else:
+            n_init = 2 if self._first_step == 0.0 else 1
         return n_init + self.n_stages * (self.n_accepted + self.n_rejected)
 
     def _set(self, field, value):
@@ -327,7 +349,7 @@ class Ensemble:
     def reset(self):
         """Re-run the constructor math (FSAL seed, select_initial_step) on the resident inputs (async)."""
         check(self._L.ni_ensemble_reset(self._h, self.rtol.ctypes.data_as(_lib._dp),
-                                        self.atol.ctypes.data_as(_lib._dp), self.max_step, self._first_step))
+                                        self.atol.ctypes.data_as(_lib._dp), self._max_step, self._first_step))
 
     def run_async(self):
         check(self._L.ni_ensemble_run_async(self._h))
@@ -351,6 +373,13 @@ class Ensemble:
         buf = _host_buffer(out, np.dtype(dt), self.N * comps, f'fetch(field {field})', writable=True)
         check(self._L.ni_ensemble_get(self._h, field, _ptr(buf)))
         return out
+
+    def compaction(self, park_below=-1):
+        """Set the tail-compaction threshold (0 disables: the default; 1..32; < 0 leaves it) and return the number of
+        trajectories that were parked for a later launch in the most recent run (ni_ensemble_compaction)."""
+        parked = C.c_int64(0)
+        check(self._L.ni_ensemble_compaction(self._h, int(park_below), parked))
+        return parked.value
 
     # ------------------------------------------------------------------ terminal records (final gather)
     def terminal_dtype(self):

@@ -488,6 +488,7 @@ struct PinnedSlots {
 PinnedSlots g_pinned;
 }  // namespace
 
+#define NI_PASSES 3
 struct ni_ensemble {
   ni_module mod;  // copy of the module description (kernels stay valid while the module lives)
   int device = 0;
@@ -500,11 +501,19 @@ struct ni_ensemble {
   std::vector<void *> allocs;
   double *y0_rows = nullptr, *t0_d = nullptr, *tb0_d = nullptr, *params_rows = nullptr;
   double *tb_saved = nullptr;
+  double *max_step_d = nullptr, *first_step_d = nullptr;  // per-trajectory step limits (allocated on first use)
   unsigned char *flag_d = nullptr;
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
   bool uploaded = false, initialised = false;
   int64_t max_attempts = 1ll << 40;
+  // tail compaction (thread-per-trajectory kernels, fast-forward launches of ensembles that fill the GPU): the run is
+  // NI_PASSES launches; pass k works on the trajectories pass k-1 parked (park_list[k-1], count = queue_all[8(k-1)+4])
+  unsigned long long *queue_all = nullptr;  // NI_PASSES x 8 counters; a.queue points at the current pass
+  unsigned int *park_list[2] = {nullptr, nullptr};
+  int64_t park_cap = 0;
+  int park_below = 0;                       // 0: no compaction (the default, see ni_ensemble_compaction); NI_B200_PARK_BELOW
+  int last_passes = 1;                      // launches of the most recent run
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t n_launches = 0;
   bool have_init_t = false, have_run_t = false;
@@ -613,7 +622,8 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
   NI_TRY(dalloc(e, &a.running, sN))
   NI_TRY(dalloc(e, &a.cond_hit, sN))
   NI_TRY(dalloc(e, &a.step_rejected, sN))
-  NI_TRY(dalloc(e, &a.queue, 8))
+  NI_TRY(dalloc(e, &e->queue_all, 8 * NI_PASSES))
+  a.queue = e->queue_all;
   NI_TRY(dalloc(e, &a.rec_cursor, 1))
   NI_TRY(dalloc(e, &e->y0_rows, sN * n))
   NI_TRY(dalloc(e, &e->t0_d, sN))
@@ -661,6 +671,22 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
     if (want >= 1 && want < nb) nb = want;
   }
   e->blocks_per_sm = nb;
+  if (const char *env = getenv("NI_B200_PARK_BELOW")) {
+    const int want = atoi(env);
+    if (want >= 0 && want <= 32) e->park_below = want;
+  }
+  if (m->kind == NI_KIND_SMALL) {
+    // a warp parks at most 31 trajectories per pass
+    const int64_t warps = (int64_t)e->sms * nb * ((m->block + 31) / 32);
+    e->park_cap = warps * 31 < N ? warps * 31 : N;
+    for (int k = 0; k < 2 && rc == NI_OK; ++k) rc = dalloc(e, &e->park_list[k], (size_t)e->park_cap);
+    if (rc != NI_OK) {
+      std::string keep = g_err;
+      ni_ensemble_destroy(e);
+      g_err = keep;
+      return rc;
+    }
+  }
   e->q_host = g_pinned.get();
   *out = e;
   return NI_OK;
@@ -679,6 +705,42 @@ NI_API int ni_ensemble_set_stream(ni_ensemble *e, void *cuda_stream) {
 NI_API int ni_ensemble_set_max_attempts(ni_ensemble *e, int64_t per_launch) {
   if (!e || per_launch < 1) return fail(NI_ERR_INVALID, "need an ensemble and per_launch >= 1");
   e->max_attempts = per_launch;
+  return NI_OK;
+}
+
+// Per-trajectory max_step / first_step (the reference takes them per solver object, _basic.py:292-299 / 323-330).
+// NULL keeps / restores the scalar of ni_ensemble_reset.  Host arrays of N doubles, copied asynchronously: they must
+// stay valid until the next synchronising call; takes effect at the next ni_ensemble_reset / run.
+NI_API int ni_ensemble_set_step_limits(ni_ensemble *e, const double *max_step, const double *first_step) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  const size_t N = (size_t)e->N;
+  if (max_step) {
+    if (!e->max_step_d)
+      if (int rc = dalloc(e, &e->max_step_d, N)) return rc;
+    CU(cudaMemcpyAsync(e->max_step_d, max_step, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (first_step) {
+    if (!e->first_step_d)
+      if (int rc = dalloc(e, &e->first_step_d, N)) return rc;
+    CU(cudaMemcpyAsync(e->first_step_d, first_step, sizeof(double) * N, cudaMemcpyHostToDevice, e->stream));
+  }
+  e->a.max_step_v = max_step ? e->max_step_d : nullptr;
+  e->a.first_step_v = first_step ? e->first_step_d : nullptr;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_compaction(ni_ensemble *e, int park_below, int64_t *parked_last_run) {
+  if (!e || park_below > 32) return fail(NI_ERR_INVALID, "need an ensemble and park_below <= 32");
+  CU(cudaSetDevice(e->device));
+  if (park_below >= 0) e->park_below = park_below;
+  if (parked_last_run) {
+    unsigned long long all[8 * NI_PASSES];
+    CU(cudaMemcpyAsync(all, e->queue_all, sizeof all, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *parked_last_run = 0;
+    for (int k = 0; k < e->last_passes; ++k) *parked_last_run += (int64_t)all[8 * k + 4];
+  }
   return NI_OK;
 }
 
@@ -771,7 +833,15 @@ NI_API int ni_ensemble_init(ni_ensemble *e, const double *t0, int t0_per_traj, c
   return ni_ensemble_sync(e);
 }
 
-// one launch of the run kernel; counters are left in a.queue
+// Number of launches of one fast-forward run: 1, or NI_PASSES when the tail is compacted (the ensemble fills the
+// resident grid at least twice -- smaller ones have no steady state to protect -- and nothing bounds the launch).
+static int run_passes(const ni_ensemble *e, int64_t max_accepts) {
+  if (e->mod.kind != NI_KIND_SMALL || e->park_below <= 0 || max_accepts < 0x7fffffffLL) return 1;
+  const int64_t lanes = (int64_t)e->sms * e->blocks_per_sm * e->mod.block;
+  return e->N >= 2 * lanes ? NI_PASSES : 1;
+}
+
+// one run of the run kernel (a single launch, or the passes of a compacted run); counters are left in e->queue_all
 static int launch_run(ni_ensemble *e, int64_t max_accepts, bool timed) {
   if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
   e->a.max_accepts = max_accepts;
@@ -779,10 +849,25 @@ static int launch_run(ni_ensemble *e, int64_t max_accepts, bool timed) {
   // record slots: warps of a long fast-forward reserve 512 at a time (one global cursor cannot serve ~1e9
   // reservations/s); lock-step calls and small ensembles reserve exactly what they write
   e->a.rec_chunk = (max_accepts == 1 || e->N < 65536 || e->mod.kind != NI_KIND_SMALL) ? 0 : 512;
-  CU(cudaMemsetAsync(e->a.queue, 0, sizeof(unsigned long long) * 8, e->stream));
+  CU(cudaMemsetAsync(e->queue_all, 0, sizeof(unsigned long long) * 8 * NI_PASSES, e->stream));
   const bool rec = e->a.rec_cap > 0;
+  const int passes = run_passes(e, max_accepts);
+  e->last_passes = passes;
   if (timed) CU(cudaEventRecord(e->ev[2], e->stream));
-  if (int rc = launch(e, e->mod.k_run[rec ? 1 : 0], run_grid(e), e->mod.block, e->mod.smem)) return rc;
+  int rc = NI_OK;
+  for (int k = 0; k < passes && rc == NI_OK; ++k) {
+    e->a.queue = e->queue_all + 8 * k;
+    e->a.work_list = k == 0 ? nullptr : e->park_list[(k - 1) & 1];
+    e->a.work_count = k == 0 ? nullptr : e->queue_all + 8 * (k - 1) + 4;
+    e->a.park_list = e->park_list[k & 1];
+    e->a.park_below = k + 1 < passes ? e->park_below : 0;  // the last pass finishes everything it holds
+    rc = launch(e, e->mod.k_run[rec ? 1 : 0], run_grid(e), e->mod.block, e->mod.smem);
+  }
+  e->a.queue = e->queue_all;
+  e->a.work_list = nullptr;
+  e->a.work_count = nullptr;
+  e->a.park_below = 0;
+  if (rc != NI_OK) return rc;
   if (timed) {
     CU(cudaEventRecord(e->ev[3], e->stream));
     e->have_run_t = true;
@@ -790,11 +875,22 @@ static int launch_run(ni_ensemble *e, int64_t max_accepts, bool timed) {
   return NI_OK;
 }
 
+// counters of the last run: [0] cursor of the first pass, [1] flags (OR over the passes), [2] trajectories that left a
+// pass still RUNNING without being parked for the next one (budget exhausted, record log full), [3] accepted lock-steps
 static int read_queue(ni_ensemble *e, unsigned long long q[4]) {
   unsigned long long *dst = e->q_host ? e->q_host : e->q_pageable;
-  CU(cudaMemcpyAsync(dst, e->a.queue, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
+  unsigned long long more[8 * (NI_PASSES - 1)];
+  const int passes = e->last_passes;
+  CU(cudaMemcpyAsync(dst, e->queue_all, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (passes > 1)
+    CU(cudaMemcpyAsync(more, e->queue_all + 8, sizeof(unsigned long long) * 8 * (passes - 1), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   for (int i = 0; i < 4; ++i) q[i] = dst[i];
+  for (int k = 1; k < passes; ++k) {
+    q[1] |= more[8 * (k - 1) + 1];
+    q[2] += more[8 * (k - 1) + 2];
+    q[3] += more[8 * (k - 1) + 3];
+  }
   return NI_OK;
 }
 
@@ -821,7 +917,7 @@ static int step_with_graph(ni_ensemble *e, unsigned long long q[4], bool *used) 
       cudaGetLastError();
       return NI_OK;  // not capturable: direct launches
     }
-    cudaMemsetAsync(e->a.queue, 0, sizeof(unsigned long long) * 8, e->stream);
+    cudaMemsetAsync(e->queue_all, 0, sizeof(unsigned long long) * 8 * NI_PASSES, e->stream);
     void *args[] = {(void *)&e->a};
     cudaLaunchKernel(kernel, dim3((unsigned)run_grid(e)), dim3((unsigned)e->mod.block), args, e->mod.smem, e->stream);
     cudaMemcpyAsync(e->q_host, e->a.queue, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream);

@@ -81,13 +81,22 @@ struct NiArgs {
   int t0_stride, tb_stride;     // 0 (scalar) or 1 (per trajectory)
   const double *params_rows;    // init only: N x P row-major
   double max_step, first_step;
+  const double *max_step_v, *first_step_v;  // per-trajectory values (N entries) that override the scalars, or NULL
   double rtol[NI_MAX_SMALL_N], atol[NI_MAX_SMALL_N];
   int n;                        // large kernels: state dimension (run-time)
   const double *rtol_d, *atol_d;  // large kernels: tolerance vectors in HBM (n entries)
   int tol_uniform;              // large kernels: every component has rtol[0] / atol[0]
   int compat;                   // 0: the reference's step semantics; 1: scipy.integrate semantics
   unsigned char *step_rejected; // compat == 1: "a rejection happened in the current step" (scipy's step_rejected)
-  unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted
+  unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted,
+                                // [4] #trajectories parked for the next compaction pass
+  // compaction of the tail: once the queue is empty a warp with fewer than `park_below` busy
+  // lanes parks its trajectories (state written back, index appended to `park_list`) and leaves; the next pass runs
+  // the parked trajectories of all warps in full warps: its work items are `work_list[0 .. *work_count)`.
+  const unsigned int *work_list;           // NULL: the work items are the trajectories 0 .. N-1
+  const unsigned long long *work_count;    // device counter written by the previous pass (its queue[4])
+  unsigned int *park_list;
+  int park_below;                          // 0: never park
   long long max_attempts;       // per trajectory per launch (bounds kernel time)
   long long max_accepts;        // 1 = lock-step ni.step(), huge = fast-forward
   // recording of accepted steps (append log, SoA, capacity rec_cap records)
@@ -103,6 +112,10 @@ struct NiArgs {
   unsigned char *cond_hit;
   double cond_params[8];        // cond_kind == 5: parameters of the user predicate
 };
+
+// max_step / first_step of trajectory idx (_basic.py:292-299: per-object arguments of the reference's factories)
+NI_DEV double ni_max_step(const NiArgs &a, long long idx) { return a.max_step_v ? a.max_step_v[idx] : a.max_step; }
+NI_DEV double ni_first_step(const NiArgs &a, long long idx) { return a.first_step_v ? a.first_step_v[idx] : a.first_step; }
 
 // Arithmetic policy.  Strict (FAST = false): every element-wise expression is evaluated unfused, as numba
 // evaluates it in the reference (bit-identical results).  Fast: multiply-adds are
@@ -473,8 +486,9 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
     Rhs::template eval<false>(t0, y, p, f0, aux);
     const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
     double h_abs;
-    if (a.first_step != 0.0) {
-      h_abs = fabs(a.first_step);
+    const double first_step = ni_first_step(a, idx);
+    if (first_step != 0.0) {
+      h_abs = fabs(first_step);
     } else if (a.compat != 0) {
       // scipy.integrate._ivp.common.select_initial_step: no fastmath contractions, h0 capped by the interval,
       // h1 = (0.01 / max(d1, d2)) ** (1 / (order + 1)), result capped by the interval and max_step
@@ -500,7 +514,7 @@ NI_DEV void ni_small_init_body(const NiArgs &a) {
       const double d2 = ni_rms<n>(tmp) / h0;
       const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, __dmul_rn(h0, 1e-3))
                                                      : pow(0.01 / fmax(d1, d2), 1.0 / (NiTab<METHOD>::ORDER + 1));
-      h_abs = interval == 0.0 ? 0.0 : fmin(fmin(__dmul_rn(100.0, h0), h1), fmin(interval, a.max_step));
+      h_abs = interval == 0.0 ? 0.0 : fmin(fmin(__dmul_rn(100.0, h0), h1), fmin(interval, ni_max_step(a, idx)));
     } else {
       double scale[n], tmp[n];
 #pragma unroll
@@ -584,12 +598,15 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
   constexpr unsigned FULL = 0xffffffffu;
   const long long N = a.N;
   const unsigned lane = threadIdx.x & 31u;
+  const long long n_work = a.work_list ? (long long)*a.work_count : N;
   const int max_att = a.max_attempts > 0x7fffffffLL ? 0x7fffffff : (int)a.max_attempts;
   const int max_acc = a.max_accepts > 0x7fffffffLL ? 0x7fffffff : (int)a.max_accepts;
 
   long long idx = 0;
   bool active = false, exhausted = false, need = true, last_accept = false, parked = false, srej = false;
+  bool compact = false;  // this lane's trajectory goes to the next compaction pass
   double t = 0, h_abs = 0, tb = 0, dir = 1, step_h = 0;
+  double mxs = a.max_step;  // max_step of the lane's trajectory (MAXS / scipy bodies)
   double y[n], kl[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
 #pragma unroll
   for (int i = 0; i < n; ++i) y[i] = kl[i] = 0.0;
@@ -643,7 +660,12 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
           a.n_rej[idx] += n_counted - n_accepted;
           a.running[idx] = last_accept ? 1 : 0;
           if (SP) a.step_rejected[idx] = srej ? 1 : 0;
-          if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
+          if (compact) {
+            a.park_list[atomicAdd(a.queue + 4, 1ull)] = (unsigned int)idx;
+            compact = false;
+          } else if (status == NI_ST_RUNNING && !parked) {
+            atomicAdd(a.queue + 2, 1ull);
+          }
           if (last_accept) atomicAdd(a.queue + 3, 1ull);
           active = false;
         }
@@ -655,10 +677,11 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
           if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(grp));
           base = __shfl_sync(grp, base, leader);
           idx = (long long)(base + __popc(grp & ((1u << lane) - 1u)));
-          if (idx >= N || (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW))) {
+          if (idx >= n_work || (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW))) {
             exhausted = true;
             break;
           }
+          if (a.work_list) idx = a.work_list[idx];
           status = a.status[idx];
           if (COND && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
           if (status != NI_ST_RUNNING) {
@@ -676,6 +699,7 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
             continue;
           }
           step_h = a.step_size[idx];
+          if (MAXS || SP) mxs = ni_max_step(a, idx);
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             y[i] = a.y[i * N + idx];
@@ -698,6 +722,20 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
         }
         need = false;
       }
+      if (a.park_below > 0) {
+        // compaction: the queue is empty and this warp is mostly idle -- hand its trajectories to the next pass,
+        // where they share full warps with the leftovers of the other warps (the state between two attempts is
+        // exactly t, y, h_abs, K[-1]: the regular retire path above writes it back on the next turn)
+        const int nact = __popc(__ballot_sync(FULL, active));
+        if (nact > 0 && nact < a.park_below && __any_sync(FULL, exhausted)) {
+          exhausted = true;
+          if (active) {
+            need = true;
+            compact = true;
+          }
+          continue;
+        }
+      }
       if (__all_sync(FULL, !active)) break;
     }
 
@@ -710,14 +748,14 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
     // (h_abs, min_step, max_step are >= +0: integer-pipe comparisons, ni_lt_pos)
     if (SP) {
       // first attempt of a step <=> no rejection seen in it yet (also right after resuming a parked trajectory)
-      if (!srej) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
+      if (!srej) h_abs = h_abs > mxs ? mxs : (h_abs < min_step ? min_step : h_abs);
     } else {
       h_abs = ni_lt_pos(h_abs, min_step) ? min_step : h_abs;
     }
     // ---- one attempt (_basic.py:145-169)
     const double h_pre = h_abs;
     const bool sp_fail = SP && h_abs < min_step;  // scipy tests the step size BEFORE every attempt, commits nothing
-    if (!SP && MAXS && ni_lt_pos(a.max_step, h_abs)) h_abs = __dadd_rn(a.max_step, -eps);
+    if (!SP && MAXS && ni_lt_pos(mxs, h_abs)) h_abs = __dadd_rn(mxs, -eps);
     // h_abs * direction (_advanced.py:163) with direction = +-1: a sign flip on the integer pipe, bit for bit the product
     double h = (ADV || SP) ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
                            : h_abs;
@@ -935,14 +973,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
   int kx = 0, tbk = 0x7fffffff;  // reach key: (hi(tn) ^ kx) >= tbk  <=  direction * (tn - t_bound) >= 0
   int xs = 0;                    // hi(h_abs) <u xs  <=  h_abs may be below 8 ulp(t) of this or the next step
 
-  for (;;) {
-    // ================================================================ SERVICE (rare)
-    if (__any_sync(FULL, svc)) {
-      // exit: the cold block latched a failure, or the last accepted step ended on t_bound (the reference's own test
-      // at the top of its next step() call, _basic.py:135)
-      if (active && (status != NI_ST_RUNNING || __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0)) {
+  const long long n_work = a.work_list ? (long long)*a.work_count : N;
+  // write the lane's trajectory back: it has finished / failed, or (`parking`) it moves to the next compaction pass
+  auto retire = [&](bool parking) {
         const int n_attempts = (int)(iter - it0);
-        if (status == NI_ST_RUNNING) {
+        if (status == NI_ST_RUNNING && !parking) {
           status = NI_ST_FINISHED;
           // the terminal step() call of `while step(): pass` (_basic.py:135-136) overwrites step_size
           step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
@@ -973,8 +1008,16 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         a.n_acc[idx] += nacc;
         a.n_rej[idx] += n_attempts - nacc;
         a.running[idx] = 0;
+        if (parking) a.park_list[atomicAdd(a.queue + 4, 1ull)] = (unsigned int)idx;
         active = false;
-      }
+  };
+
+  for (;;) {
+    // ================================================================ SERVICE (rare)
+    if (__any_sync(FULL, svc)) {
+      // exit: the cold block latched a failure, or the last accepted step ended on t_bound (the reference's own test
+      // at the top of its next step() call, _basic.py:135)
+      if (active && (status != NI_ST_RUNNING || __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0)) retire(false);
       // refill: pop trajectories (warp-aggregated) until one is runnable or the queue is empty
       while (!active && !exhausted) {
         const unsigned grp = __activemask();
@@ -983,10 +1026,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(grp));
         base = __shfl_sync(grp, base, leader);
         idx = (long long)(base + __popc(grp & ((1u << lane) - 1u)));
-        if (idx >= N) {
+        if (idx >= n_work) {
           exhausted = true;
           break;
         }
+        if (a.work_list) idx = a.work_list[idx];
         status = a.status[idx];
         if (status != NI_ST_RUNNING) {
           a.running[idx] = 0;  // step() on a finished / failed solver returns False
@@ -1022,6 +1066,16 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         nacc = 0;
         it0 = iter;
         active = true;
+      }
+      if (a.park_below > 0) {
+        // compaction: the queue is empty and this warp is mostly idle -- its trajectories go to the next pass, where
+        // they share full warps with the leftovers of the other warps (the state between two attempts is exactly
+        // t, y, h_abs, K[-1])
+        const int nact = __popc(__ballot_sync(FULL, active));
+        if (nact > 0 && nact < a.park_below && __any_sync(FULL, exhausted)) {
+          if (active) retire(true);
+          exhausted = true;
+        }
       }
       if (active) {
         // ---- exact step entry (_basic.py:139-156) of the coming attempt
@@ -1130,7 +1184,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
 
 template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
-  const bool no_max_step = __double_as_longlong(a.max_step) == 0x7ff0000000000000LL;
+  const bool no_max_step = __double_as_longlong(a.max_step) == 0x7ff0000000000000LL && a.max_step_v == nullptr;
   if constexpr (NI_LEAN && SEM != 2 && !REC && NI_COND == 0) {
     // fast-forward without an attempt budget and with max_step = inf; lock-step ni.step takes the general body
     if (no_max_step && a.max_attempts >= 0x7fffffffLL && a.max_accepts >= 0x7fffffffLL)

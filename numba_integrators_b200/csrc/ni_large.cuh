@@ -236,7 +236,8 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
     ni_large_rhs<Rhs, CPT, false>(c, t0, y, p, 0, f0);
     const double dir = tb != t0 ? (tb > t0 ? 1.0 : -1.0) : 1.0;
     double h_abs;
-    if (a.first_step == 0.0) {
+    const double first_step = ni_first_step(a, idx);
+    if (first_step == 0.0) {
       // reference: numba fastmath contracts `scale` and `y1` to FMAs; scipy semantics
       // (a.compat): unfused, h0 capped by the interval, h1 = (0.01 / max(d1, d2)) ** (1 / (order + 1)), result capped
       // by the interval and max_step
@@ -270,9 +271,9 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
       else
         h1 = ni_pow_init<NiTab<METHOD>::ORDER + 1>(__dmul_rn(fmax(d1, d2), 100.0));
       h_abs = fmin(__dmul_rn(100.0, h0), h1);
-      if (sp) h_abs = interval == 0.0 ? 0.0 : fmin(h_abs, fmin(interval, a.max_step));
+      if (sp) h_abs = interval == 0.0 ? 0.0 : fmin(h_abs, fmin(interval, ni_max_step(a, idx)));
     } else {
-      h_abs = fabs(a.first_step);
+      h_abs = fabs(first_step);
     }
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
@@ -332,7 +333,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       continue;
     }
     double t = a.t[idx], h_abs = a.h_abs[idx], step_h = a.step_size[idx];
-    const double tb = a.t_bound[idx], dir = a.direction[idx];
+    const double tb = a.t_bound[idx], dir = a.direction[idx], mxs = ni_max_step(a, idx);
     double y[CPT], k0[CPT], kr[NiLargeRegs<METHOD>::COUNT][CPT], p[P > 0 ? P : 1];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
@@ -361,7 +362,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         eps = ni_ulp_eps(t, dir);
         min_step = __dmul_rn(SP ? 10.0 : 8.0, eps);
         if (SP) {
-          if (!srej) h_abs = h_abs > a.max_step ? a.max_step : (h_abs < min_step ? min_step : h_abs);
+          if (!srej) h_abs = h_abs > mxs ? mxs : (h_abs < min_step ? min_step : h_abs);
         } else if (h_abs < min_step) {
           h_abs = min_step;
         }
@@ -374,7 +375,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         last_accept = false;
         break;
       }
-      if (!SP && h_abs > a.max_step) h_abs = __dadd_rn(a.max_step, -eps);
+      if (!SP && h_abs > mxs) h_abs = __dadd_rn(mxs, -eps);
       double h = (ADV || SP) ? __dmul_rn(h_abs, dir) : h_abs;
       double tn = __dadd_rn(t, h);
       {

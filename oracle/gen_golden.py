@@ -176,11 +176,24 @@ def _make_runner(direct):
 RUN = {m: _make_runner(d) for m, d in DIRECT.items()}
 
 
+ONLY = None  # names (prefixes) given on the command line: generate just those cases
+
+
+def _wanted(name):
+    return ONLY is None or any(name.startswith(p) for p in ONLY)
+
+
 def run_case(name, rhs, method, t0, y0, params, t_bound, rtol, atol, max_step=np.inf, first_step=0.0,
              rec_cap=0, rec_traj=0, max_steps=10 ** 9, note=''):
-    """Run every row of y0 through the reference's Advanced solver and save inputs + outputs."""
+    """Run every row of y0 through the reference's Advanced solver and save inputs + outputs.
+    max_step / first_step may be arrays: one value per trajectory (the reference takes them per solver object)."""
+    if not _wanted(name):
+        return
     y0 = np.atleast_2d(np.asarray(y0, np.float64))
     N, n = y0.shape
+    per_traj_limits = np.ndim(max_step) > 0 or np.ndim(first_step) > 0
+    ms_v = np.broadcast_to(np.asarray(max_step, np.float64), (N,)).copy()
+    fs_v = np.broadcast_to(np.asarray(first_step, np.float64), (N,)).copy()
     params = np.zeros((N, 0)) if params is None else np.asarray(params, np.float64).reshape(N, -1)
     t0a = np.broadcast_to(np.asarray(t0, np.float64), (N,)).copy()
     tba = np.broadcast_to(np.asarray(t_bound, np.float64), (N,)).copy()
@@ -195,10 +208,10 @@ def run_case(name, rhs, method, t0, y0, params, t_bound, rtol, atol, max_step=np
     for i in range(N):
         cap = rec_cap if i < R else 0
         t, y, a, h_abs, step_size, k, nfev, h0, a0, rt_, ry_, rh_ = run(
-            fun, t0a[i], y0[i], params[i], tba[i], float(max_step), rt, at, float(first_step), cap, max_steps)
+            fun, t0a[i], y0[i], params[i], tba[i], float(ms_v[i]), rt, at, float(fs_v[i]), cap, max_steps)
         o['t'][i], o['y'][i], o['h_abs'][i], o['step_size'][i], o['h_abs0'][i] = t, y, h_abs, step_size, h0
         o['n_accepted'][i], o['nfev'][i] = k, nfev
-        n_init = 2 if first_step == 0.0 else 1
+        n_init = 2 if fs_v[i] == 0.0 else 1
         att = (nfev - n_init) / S_PRIME[method]
         assert att == int(att), (nfev, n_init)
         o['n_rejected'][i] = int(att) - k
@@ -206,9 +219,11 @@ def run_case(name, rhs, method, t0, y0, params, t_bound, rtol, atol, max_step=np
         aux0.append(a0)
         if i < R:
             rec_t[i], rec_y[i], rec_h[i] = rt_, ry_, rh_
-    meta = dict(name=name, rhs=rhs, method=method, advanced=True, max_step=float(max_step),
-                first_step=float(first_step), rec_cap=rec_cap, rec_traj=R, max_steps=min(max_steps, 2 ** 62),
+    meta = dict(name=name, rhs=rhs, method=method, advanced=True, max_step=float(ms_v[0]),
+                first_step=float(fs_v[0]), rec_cap=rec_cap, rec_traj=R, max_steps=min(max_steps, 2 ** 62),
                 note=note, versions=dict(numba=nb.__version__, numpy=np.__version__))
+    if per_traj_limits:  # (meta carries the first trajectory's values; the arrays are authoritative)
+        o.update(max_step_v=ms_v, first_step_v=fs_v)
     np.savez_compressed(OUT / f'{name}.npz', meta=json.dumps(meta), t0=t0a, y0=y0, params=params, t_bound=tba,
                         rtol=rt, atol=at, aux=np.array(aux), aux0=np.array(aux0), rec_t=rec_t, rec_y=rec_y,
                         rec_h=rec_h, **o)
@@ -218,6 +233,8 @@ def run_case(name, rhs, method, t0, y0, params, t_bound, rtol, atol, max_step=np
 def run_basic_case(name, rhs, method, t0, y0, t_bound, rtol, atol, max_step=np.inf, first_step=0.0, n_steps=10 ** 9,
                    note=''):
     """One trajectory through the reference's BASIC solver, stepping from Python; records every step."""
+    if not _wanted(name):
+        return
     ctor = ni.RK45 if method == 'RK45' else ni.RK23
     s = ctor(BASIC_RHS[rhs], t0, np.asarray(y0, np.float64), t_bound, max_step=max_step, rtol=rtol, atol=atol,
              first_step=first_step)
@@ -311,7 +328,18 @@ def main():
     run_case('burgers64_rk45', 'burgers1d', 'RK45', 0.0, w.y0, pb, 1.0, 1e-6, 1e-8)
     w = wl.c5_heat(N=4, n=7, t_bound=3.0)
     run_case('heat7_rk23', 'heat1d', 'RK23', 0.0, w.y0, w.params, 3.0, 1e-6, 1e-8, rec_cap=64, rec_traj=1)
+    # -- per-trajectory max_step / first_step (the reference takes both per solver object, _basic.py:292-299):
+    #    unlimited / binding / very tight max_step, automatic / given first_step, mixed within one ensemble
+    w = wl.c3_lorenz(N=8, t_bound=1.0)
+    run_case('per_traj_limits_lorenz_rk45', w.rhs, 'RK45', 0.0, w.y0, w.params, 1.0, 1e-8, 1e-8,
+             max_step=[np.inf, 0.02, 0.005, np.inf, 0.011, 1.0, 0.0025, np.inf],
+             first_step=[0.0, 0.0, 1e-3, 1e-4, 0.0, 5e-3, 0.0, 2e-2], rec_cap=128, rec_traj=8)
+    w = wl.c5_heat(N=4, n=48, t_bound=0.3)
+    run_case('per_traj_limits_heat48_rk23', 'heat1d', 'RK23', 0.0, w.y0, w.params, 0.3, 1e-6, 1e-8,
+             max_step=[np.inf, 2e-3, 5e-4, np.inf], first_step=[0.0, 1e-4, 0.0, 1e-5])
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1:
+        ONLY = sys.argv[1:]
     main()

@@ -35,7 +35,10 @@ FULL_RUN = [n for n in golden_names() if load_golden(n)[0].get('n_steps', 10 ** 
 def build(meta, g, rows=slice(None), **kw):
     f = ni.BuiltinRHS(meta['rhs'])
     par = g['params'][rows]
-    args = dict(max_step=meta['max_step'], rtol=g['rtol'], atol=g['atol'], first_step=meta['first_step'], **kw)
+    # per-trajectory max_step / first_step fixtures carry arrays (the reference takes both per solver object)
+    max_step = g['max_step_v'][rows] if 'max_step_v' in g else meta['max_step']
+    first_step = g['first_step_v'][rows] if 'first_step_v' in g else meta['first_step']
+    args = dict(max_step=max_step, rtol=g['rtol'], atol=g['atol'], first_step=first_step, **kw)
     if meta['advanced']:
         ctor = ni.Advanced(f.P, f.Q, ni.RK45 if meta['method'] == 'RK45' else ni.RK23)
         return ctor(f, g['t0'][rows], g['y0'][rows], par if f.P else None, g['t_bound'][rows], **args)
@@ -70,15 +73,30 @@ def test_fast_forward_matches_reference(name):
         assert np.all(np.abs(aux - g['aux'])[ok] <= 10 * tol * np.abs(g['aux'])[ok] + 1e-300)
 
 
+# Recorded-stream tolerances: step times jitter by ~1e-11 relative once one controller `pow`
+# differs by an ulp (glibc's is misrounded in ~0.05 % of calls), so t_k agree to 1e-9 max(1, |t|) and y_k to
+# f(t_k, y_k) dt_k plus a state difference that is still ~1e-12 here.  Per-fixture exceptions would go here:
+STREAM_TOL = {}  # name -> (tol_t, tol_y); none needed: on B200 the worst |dt| is 2.5e-12, the worst |dy - f dt| 1.3e-13
+STREAM_DEFAULT = (1e-9, 1e-10)  # |dt| <= 1e-9 max(1, |t|);  |dy - f dt| <= 1e-10 max(1, |y|)
+
+
 @pytest.mark.parametrize('name', [n for n in golden_names() if load_golden(n)[1]['rec_t'].size])
-def test_lock_step_sequence_matches_reference(name):
+def test_lock_step_sequence_matches_reference(name, oracle):
     """ni.step() by ni.step(): every accepted (t, y) against the reference's recorded sequence."""
     meta, g = load_golden(name)
     R = g['rec_t'].shape[0]
     s = build(meta, g, rows=slice(0, R))
     assert np.array_equal(np.atleast_1d(s.h_abs), g['h_abs0'][:R])                    # select_initial_step, bitwise
     K = int(min(g['rec_t'].shape[1], g['n_accepted'][:R].max()))
+    tol_t, tol_y = STREAM_TOL.get(name, STREAM_DEFAULT)
+    method = oracle.RK45 if meta['method'] == 'RK45' else oracle.RK23
+
+    def rhs(i, t, y):  # f(t, y) of trajectory i: the FSAL seed of an oracle solver constructed at (t, y)
+        par = g['params'][i] if g['params'].shape[1] else None
+        return oracle.OracleSolver(meta['rhs'], method, t, y, t + 1.0, params=par, first_step=1e-3,
+                                   advanced=meta['advanced']).K[-1]
     n_cmp = n_bit = n_first_bit = 0
+    worst_t = worst_y = 0.0
     for k in range(K):
         running = np.atleast_1d(ni.step(s))
         t, y = np.atleast_1d(s.t), np.atleast_2d(s.y)
@@ -89,15 +107,17 @@ def test_lock_step_sequence_matches_reference(name):
                 if t[i] == g['rec_t'][i, k] and np.array_equal(y[i], g['rec_y'][i, k]):
                     n_bit += 1
                     n_first_bit += k == 0
-                # Once one `pow` differs by an ulp (glibc's is not correctly rounded in ~0.05 % of calls) the
-                # step-size sequence shifts: the error estimate is a cancellation at the 1e-8 tolerance level,
-                # so 1 ulp in y moves the next h by ~1e-8 relative -- intermediate
-                # (t_k, y_k) then differ by ~|f| dt while the values at t_bound agree to 1e-12.
-                assert abs(t[i] - g['rec_t'][i, k]) <= 1e-6 * max(1.0, abs(t[i])), (name, i, k)
-                assert np.all(np.abs(y[i] - g['rec_y'][i, k]) <= 1e-4 * np.maximum(1.0, np.abs(y[i]))), (name, i, k)
+                    continue
+                dt = t[i] - g['rec_t'][i, k]
+                dy = y[i] - g['rec_y'][i, k] - rhs(i, g['rec_t'][i, k], g['rec_y'][i, k]) * dt
+                et, ey = abs(dt) / max(1.0, abs(t[i])), np.max(np.abs(dy) / np.maximum(1.0, np.abs(y[i])))
+                worst_t, worst_y = max(worst_t, et), max(worst_y, ey)
+                assert et <= tol_t, (name, i, k, dt)
+                assert ey <= tol_y, (name, i, k, dy)
     # the first step of every recorded trajectory is bit-identical to the reference (init + one attempt);
     # later ones stay identical until glibc's pow first misrounds
     assert n_first_bit == R, (name, n_first_bit, R, n_bit, n_cmp)
+    print(f'{name}: {n_bit}/{n_cmp} recorded steps bit-identical, worst |dt| {worst_t:.1e}, worst |dy - f dt| {worst_y:.1e}')
 
 
 @pytest.mark.parametrize('cfg', ['c2', 'c3_t1', 'c4_tol1e-8'])
@@ -201,3 +221,39 @@ def test_large_system_fallbacks(n, oracle):
     _against_oracle(oracle, 'heat1d', 'RK45', y0, 3.0, params=k, tol=1e-10)
     # atol = 0: rows 1 and 2 only (row 0 would be 0 / 0)
     _against_oracle(oracle, 'heat1d', 'RK45', y0[1:] + 2.0, 3.0, params=k[1:], atol=0.0, tol=1e-10)
+
+
+def test_tail_compaction_is_bit_identical_and_really_parks(oracle):
+    """North-star: 'work-queue refill and compaction of finished lanes, so warps stay full'.  A fast-forward run of an
+    ensemble that fills the GPU twice over is three launches; warps that run mostly empty after the queue is exhausted
+    park their trajectories for the next launch (opt-in: ni_ensemble_compaction).  Forced with the most aggressive
+    threshold (park when fewer than 32 lanes are busy), the result must equal the single-launch run bit for bit, and
+    the oracle on the step counts (99.9 % of the Lorenz trajectories; the Van der Pol sweep has a lower floor)."""
+    from numba_integrators_b200 import workloads as wl
+    for w, method, bar in ((wl.c3_lorenz(N=400_000, t_bound=1.0), ni.RK45, 0.999),
+                           (wl.c4_vanderpol(N=400_000, t_bound=3.0, tol=1e-8), ni.RK23, 0.99)):
+        f = ni.BuiltinRHS(w.rhs)
+        runs = {}
+        for park in (0, 32, 16):
+            if w.advanced:
+                e = ni.Advanced(f.P, f.Q, method)(f, w.t0, w.y0, w.params, w.t_bound, rtol=w.rtol, atol=w.atol)
+            else:
+                e = method(f(*w.params.T), w.t0, w.y0, w.t_bound, rtol=w.rtol, atol=w.atol)
+            e.compaction(park)
+            launches0 = e.timing()['launches']
+            assert e.run() == 0
+            parked = e.compaction()
+            launches = e.timing()['launches'] - launches0
+            assert (launches, parked > 0) == ((1, False) if park == 0 else (3, True)), (park, launches, parked)
+            runs[park] = e.terminal()
+            assert np.all(runs[park]['status'] == 1)
+        for park in (32, 16):
+            assert runs[park].tobytes() == runs[0].tobytes(), f'park_below={park} changed the results'
+        k = 20_000  # oracle on a prefix + the last rows (the tail of the queue is what gets parked)
+        sel = np.r_[0:k, w.N - k:w.N]
+        ref = oracle.run_ensemble(w.rhs, oracle.RK45 if method is ni.RK45 else oracle.RK23, w.t0, w.y0[sel], w.t_bound,
+                                  params=w.params[sel], rtol=w.rtol, atol=w.atol, advanced=w.advanced)
+        got = runs[32][sel]
+        same = (got['n_accepted'] == ref['n_accepted']) & (got['n_rejected'] == ref['n_rejected'])
+        rel = np.max(np.abs(got['y'] - ref['y']), axis=1) / np.max(np.abs(ref['y']), axis=1)
+        assert np.mean(same) >= bar and np.mean(rel[same] <= 1e-12) >= bar, (w.name, np.mean(same), np.mean(rel <= 1e-12))
