@@ -121,6 +121,13 @@ int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method
  * returning dy_j; y is the whole stage vector, staged in shared memory by the CTA that owns the trajectory. */
 int ni_module_compile_component(const char *component_body, int n, int P, int method, int mode,
                                 const char *nvrtc_options, ni_module **out);
+/* General form of the two calls above: component = 0 (3-point stencil) / 1 (component-wise), plus Q auxiliary outputs
+ * (the second return value of an Advanced right-hand side, _advanced.py:22-26 / :181) computed from the WHOLE committed
+ * state by `aux_body`, the body of
+ *   __device__ void aux(double t, const double* y, int n, const double* p, double* aux)
+ * (evaluated by one thread when a trajectory leaves the kernel, per recorded step, and before a predicate). */
+int ni_module_compile_large(int component, const char *rhs_body, const char *aux_body, int n, int P, int Q, int method,
+                            int mode, const char *nvrtc_options, ni_module **out);
 int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *mode, int *n_stages);
 /* device layout of the y / klast / aux / params buffers behind ni_ensemble_device_ptr:
  * 0 = component-major [n][N] (thread-per-trajectory kernels), 1 = trajectory-major [N][n] (CTA-per-trajectory) */
@@ -154,10 +161,16 @@ int ni_ensemble_set_step_limits(ni_ensemble *e, const double *max_step, const do
  * *n_true = number of trajectories whose step() returned True. */
 int ni_ensemble_step(ni_ensemble *e, int64_t *n_true);
 /* `while ni.step(solver): pass` on every trajectory.  *n_unfinished = trajectories still
- * RUNNING when the call returns (0 unless the record log filled up -> NI_ERR_REC_OVERFLOW). */
+ * RUNNING when the call returns (0 unless the record log filled up -> NI_ERR_REC_OVERFLOW).  Trajectories that ended
+ * FAILED / NONFINITE are not "unfinished": ni_ensemble_poll counts them, NI_F_STATUS names them. */
 int ni_ensemble_run(ni_ensemble *e, int64_t *n_unfinished);
-int ni_ensemble_run_async(ni_ensemble *e); /* one launch, no host synchronisation */
+int ni_ensemble_run_async(ni_ensemble *e); /* the same launch(es), no host synchronisation: ni_ensemble_poll tells how it ended */
 int ni_ensemble_sync(ni_ensemble *e);
+/* Synchronises and reports how the most recent run / run_async / step ended: *n_unfinished = trajectories still RUNNING
+ * (attempt budget used up, record log full), *n_failed = trajectories that left with status FAILED (step size below
+ * 8 ulp(t), _basic.py:179-180) or NONFINITE; returns NI_ERR_REC_OVERFLOW when the record log filled up.  Either
+ * pointer may be NULL. */
+int ni_ensemble_poll(ni_ensemble *e, int64_t *n_unfinished, int64_t *n_failed);
 /* ni.ff2t (_API.py:27-39).  is_not_last: uint8[N] host buffer or NULL. */
 int ni_ensemble_ff2t(ni_ensemble *e, double t_end, uint8_t *is_not_last);
 /* ni.ff2cond (_API.py:41-49) with a built-in threshold predicate NI_COND_* (y[index] or aux[index] against `value`);
@@ -168,7 +181,8 @@ int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double value, 
 /* ni.ff2cond with a user predicate (_API.py:41-49 takes any njit callable): `cond_body` is the body of
  *   __device__ bool cond(double t, const double* y, const double* aux, const double* cp)
  * fused (NVRTC) into this ensemble's run kernel and evaluated after every accepted step; cp = cond_params
- * (0..8 doubles).  Thread-per-trajectory kernels only. */
+ * (0..8 doubles).  CTA-per-trajectory kernels evaluate it on one thread, `y` being the whole state vector staged in
+ * shared memory. */
 int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const double *cond_params, int n_params,
                              uint8_t *hit, int64_t *n_hit);
 

@@ -35,6 +35,8 @@ SIGNATURES = {
                                     C.POINTER(_vp)]),
     'ni_module_compile_stencil': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)]),
     'ni_module_compile_component': (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_vp)]),
+    'ni_module_compile_large': (C.c_int, [C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_char_p, C.POINTER(_vp)]),
     'ni_module_info': (C.c_int, [_vp] + [C.POINTER(C.c_int)] * 6),
     'ni_module_layout': (C.c_int, [_vp, C.POINTER(C.c_int)]),
     'ni_module_log': (C.c_char_p, [_vp]),
@@ -49,6 +51,7 @@ SIGNATURES = {
     'ni_ensemble_run': (C.c_int, [_vp, _i64p]),
     'ni_ensemble_run_async': (C.c_int, [_vp]),
     'ni_ensemble_sync': (C.c_int, [_vp]),
+    'ni_ensemble_poll': (C.c_int, [_vp, _i64p, _i64p]),
     'ni_ensemble_ff2t': (C.c_int, [_vp, C.c_double, _vp]),
     'ni_ensemble_ff2cond': (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, _vp, _i64p]),
     'ni_ensemble_ff2cond_user': (C.c_int, [_vp, C.c_char_p, _dp, C.c_int, _vp, _i64p]),

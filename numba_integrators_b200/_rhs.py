@@ -98,57 +98,57 @@ class CudaRHS(RHS):
         return f'CudaRHS({self.name!r}, n={self.n}, P={self.P}, Q={self.Q})'
 
 
-class CudaStencilRHS(RHS):
+class _CudaLargeRHS(RHS):
+    """Common part of the CTA-per-trajectory snippets: an optional auxiliary function over the whole state,
+
+        __device__ void aux(double t, const double* y, int n, const double* p, double* aux)
+
+    writing Q outputs (the second return value of an Advanced right-hand side, _advanced.py:22-26)."""
+    shared_module = True
+    _component = 0
+
+    def __init__(self, body, P=0, parameters=None, name=None, nvrtc_options='', aux_body=None, Q=0):
+        self.body, self.P, self.Q, self.n = str(body), int(P), int(Q), None
+        self.name = name or ('user_component' if self._component else 'user_stencil')
+        if bool(self.Q) != bool(aux_body):
+            raise ValueError('Q auxiliary outputs need an aux_body (and the other way round)')
+        self.aux_body = None if aux_body is None else str(aux_body)
+        self.nvrtc_options = nvrtc_options
+        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
+
+    def _module(self, n, method, mode):
+        def make():
+            out = _lib._vp()
+            _lib.check(_lib.lib().ni_module_compile_large(self._component, self.body.encode(),
+                                                          None if self.aux_body is None else self.aux_body.encode(),
+                                                          int(n), self.P, self.Q, int(method), int(mode),
+                                                          self.nvrtc_options.encode(), out))
+            return out
+        return _cached_module((self._component, self.body, self.aux_body, int(n), self.P, self.Q, int(method), int(mode),
+                               self.nvrtc_options), make)
+
+    def __repr__(self):
+        return f'{type(self).__name__}({self.name!r}, P={self.P}, Q={self.Q})'
+
+
+class CudaStencilRHS(_CudaLargeRHS):
     """User right-hand side of a large 1-D method-of-lines system (n <= 4096): the body of
 
         __device__ double rhs_j(double t, double ym, double yc, double yp, const double* p, int j, int n)
 
     returning dy_j from y_{j-1}, y_j, y_{j+1} (zero outside 0..n-1).  Fused into the CTA-per-trajectory
     kernels with NVRTC; n is taken from y0."""
-
-    shared_module = True
-
-    def __init__(self, body, P=0, parameters=None, name='user_stencil', nvrtc_options=''):
-        self.body, self.P, self.Q, self.n, self.name = str(body), int(P), 0, None, name
-        self.nvrtc_options = nvrtc_options
-        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
-
-    def _module(self, n, method, mode):
-        def make():
-            out = _lib._vp()
-            _lib.check(_lib.lib().ni_module_compile_stencil(self.body.encode(), int(n), self.P, int(method),
-                                                            int(mode), self.nvrtc_options.encode(), out))
-            return out
-        return _cached_module(('stencil', self.body, int(n), self.P, 0, int(method), int(mode), self.nvrtc_options), make)
-
-    def __repr__(self):
-        return f'CudaStencilRHS({self.name!r}, P={self.P})'
+    _component = 0
 
 
-class CudaComponentRHS(RHS):
+class CudaComponentRHS(_CudaLargeRHS):
     """User right-hand side of a large system (17 <= n <= 4096 is where it pays) with arbitrary coupling, written
     component-wise: the body of
 
         __device__ double rhs_j(double t, const double* y, int j, int n, const double* p)
 
     returning dy_j.  One CTA integrates one trajectory; `y` is the stage vector in shared memory."""
-    shared_module = True
-
-    def __init__(self, body, P=0, parameters=None, name='user_component', nvrtc_options=''):
-        self.body, self.P, self.Q, self.n, self.name = str(body), int(P), 0, None, name
-        self.nvrtc_options = nvrtc_options
-        self.bound_parameters = None if parameters is None else np.asarray(parameters, dtype=np.float64)
-
-    def _module(self, n, method, mode):
-        def make():
-            out = _lib._vp()
-            _lib.check(_lib.lib().ni_module_compile_component(self.body.encode(), int(n), self.P, int(method),
-                                                              int(mode), self.nvrtc_options.encode(), out))
-            return out
-        return _cached_module(('component', self.body, int(n), self.P, 0, int(method), int(mode), self.nvrtc_options), make)
-
-    def __repr__(self):
-        return f'CudaComponentRHS({self.name!r}, P={self.P})'
+    _component = 1
 
 
 harmonic = BuiltinRHS('harmonic')

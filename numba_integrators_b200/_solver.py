@@ -303,8 +303,16 @@ class Ensemble:
             return bool(n_true.value)
         return _mask(self._get(_lib.F_RUNNING, None, np.uint8))
 
+    def poll(self):
+        """Synchronise and report how the last run / run_async / step ended: (unfinished, failed) trajectory counts --
+        still RUNNING (attempt budget, full record log) and FAILED / NONFINITE.  Raises NiError(-6) on a full log."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self._L.ni_ensemble_poll(self._h, a, b))
+        return a.value, b.value
+
     def run(self):
-        """`while step(): pass` for every trajectory, on the device.  Returns #trajectories not finished."""
+        """`while step(): pass` for every trajectory, on the device.  Returns the number of trajectories still RUNNING
+        (0 unless the record log filled up); failed / non-finite ones are counted by `poll()` and named by `status`."""
         left = C.c_int64(0)
         check(self._L.ni_ensemble_run(self._h, left))
         return left.value
@@ -624,7 +632,7 @@ def ff2cond(solver, condition, parameters):
         return solver.ff2cond_device(condition.kind, condition.index, parameters)
     if isinstance(condition, CudaCondition):
         return solver.ff2cond_user(condition.body, parameters)
-    if callable(condition) and solver.kind == 0:
+    if callable(condition):
         # a Python predicate: translate its source and evaluate it inside the kernel; predicates outside the
         # translatable subset fall back to the reference's own host loop over lock-step step() calls
         from ._translate import TranslationError, translate_condition

@@ -68,8 +68,9 @@ struct ni_module {
   NiLargePlan large{};       // kernel-class specific launch plan (CTA-per-trajectory)
   cudaLibrary_t lib = nullptr;  // NVRTC modules only
   std::string log;
-  std::string rhs_src;          // thread-per-trajectory modules: definition of `NiUserRhs` (recompiled with a user
-                                // predicate by ni_ensemble_ff2cond_user)
+  std::string rhs_src;          // definition of `NiUserRhs` (thread-per-trajectory) / `NiUserStencil` (CTA-per-
+                                // trajectory): recompiled with a user predicate by ni_ensemble_ff2cond_user
+  bool component = false;       // CTA-per-trajectory: component-wise (dense) right-hand side
 };
 
 static const char *builtin_functor(int rhs_id) {
@@ -98,8 +99,9 @@ static const NiKernelSet *builtin_small(int rhs_id, int n) {
   }
 }
 
-static int compile_stencil_module(const std::string &functor_src, int n, int P, int method, int mode,
-                                  const char *nvrtc_options, ni_module **out, bool component = false);
+static int compile_stencil_module(const std::string &functor_src, int n, int P, int Q, int method, int mode,
+                                  const char *nvrtc_options, ni_module **out, bool component = false,
+                                  const std::string &cond_src = std::string());
 
 NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
@@ -133,7 +135,7 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module 
     delete m;
     const int P = rhs_id == NI_RHS_HEAT1D ? 1 : 2;
     return compile_stencil_module(std::string("using NiUserStencil = ") + (rhs_id == NI_RHS_HEAT1D ? "NiStencilHeat" : "NiStencilBurgers") + ";\n",
-                                  n, P, method, mode, nullptr, out);
+                                  n, P, 0, method, mode, nullptr, out);
   }
   if (ni_large_builtin(rhs_id, n, method, advanced, &m->large, &m->P, &m->Q)) {
     m->kind = NI_KIND_LARGE;
@@ -143,6 +145,7 @@ NI_API int ni_module_builtin(int rhs_id, int n, int method, int mode, ni_module 
     m->k_run[1] = m->large.k_run[1];
     m->block = m->large.threads;
     m->smem = m->large.smem_bytes;
+    m->rhs_src = std::string("using NiUserStencil = ") + (rhs_id == NI_RHS_HEAT1D ? "NiStencilHeat" : "NiStencilBurgers") + ";\n";
     *out = m;
     return NI_OK;
   }
@@ -351,11 +354,12 @@ NI_API int ni_module_compile(const char *rhs_body, int n, int P, int Q, int meth
   return NI_OK;
 }
 
-// NVRTC build of the CTA-per-trajectory kernels for a stencil functor `NiUserStencil` defined by `functor_src`
-static int compile_stencil_module(const std::string &functor_src, int n, int P, int method, int mode,
-                                  const char *nvrtc_options, ni_module **out, bool component) {
+// NVRTC build of the CTA-per-trajectory kernels for a functor `NiUserStencil` defined by `functor_src`; with
+// `cond_src` (the definition of ni_user_cond) the run kernels carry that ff2cond predicate
+static int compile_stencil_module(const std::string &functor_src, int n, int P, int Q, int method, int mode,
+                                  const char *nvrtc_options, ni_module **out, bool component, const std::string &cond_src) {
   if (method != NI_RK23 && method != NI_RK45) return fail(NI_ERR_INVALID, "method must be NI_RK23 or NI_RK45");
-  if (P < 0) return fail(NI_ERR_INVALID, "need P >= 0");
+  if (P < 0 || Q < 0) return fail(NI_ERR_INVALID, "need P >= 0, Q >= 0");
   if (mode & ~(NI_MODE_ADVANCED | NI_MODE_FAST | NI_MODE_SCIPY)) return fail(NI_ERR_INVALID, "unknown mode bits 0x%x", mode);
   int lg = 0, threads = 0;
   size_t smem = 0;
@@ -365,7 +369,8 @@ static int compile_stencil_module(const std::string &functor_src, int n, int P, 
             scipy = (mode & NI_MODE_SCIPY) ? 1 : 0;
   const std::string M = method == NI_RK45 ? "NI_RK45" : "NI_RK23", A = scipy ? "2" : advanced ? "1" : "0",
                     F = fast ? "true" : "false", C = std::to_string(1 << lg);
-  std::string src = "#include \"ni_large.cuh\"\n" + functor_src;
+  std::string src = std::string(cond_src.empty() ? "" : "#define NI_HAVE_USER_COND 1\n") + "#include \"ni_large.cuh\"\n" +
+                    functor_src + cond_src;
   const std::string lb = "extern \"C\" __global__ void __launch_bounds__(NI_LARGE_MAX_THREADS, 1) ";
   src += lb + "ni_user_init(const NiArgs a) { extern __shared__ double s[]; ni_large_init_body<NiUserStencil, " + M +
          ", " + C + ">(a, s); }\n";
@@ -383,7 +388,7 @@ static int compile_stencil_module(const std::string &functor_src, int n, int P, 
   m->kind = NI_KIND_LARGE;
   m->n = n;
   m->P = P;
-  m->Q = 0;
+  m->Q = Q;
   m->method = method;
   m->advanced = advanced;
   m->fast = fast;
@@ -391,6 +396,8 @@ static int compile_stencil_module(const std::string &functor_src, int n, int P, 
   m->S = method == NI_RK45 ? 6 : 3;
   m->block = threads;
   m->smem = smem;
+  m->rhs_src = functor_src;
+  m->component = component;
   m->large.cpt = 1 << lg;
   m->large.threads = threads;
   m->large.smem_bytes = smem;
@@ -401,34 +408,49 @@ static int compile_stencil_module(const std::string &functor_src, int n, int P, 
   return NI_OK;
 }
 
-NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
-                                     const char *nvrtc_options, ni_module **out) {
+// Source of `NiUserStencil` for a stencil (component = 0) or component-wise (1) right-hand side body, with an optional
+// auxiliary function body over the whole state vector
+static std::string large_functor_src(int component, const char *rhs_body, const char *aux_body, int P, int Q) {
+  std::string f;
+  f += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P < 0 ? 0 : P) + ", Q = " + std::to_string(Q) + ";\n";
+  f += std::string("  static constexpr bool COMPONENT = ") + (component ? "true" : "false") + ";\n  template <bool FAST>\n";
+  if (component) {
+    f += "  NI_DEV static double eval(double t, const double* y, int j, int n, const double* p) {\n";
+    f += "    (void)t; (void)y; (void)j; (void)n; (void)p;\n";
+  } else {
+    f += "  NI_DEV static double eval(double t, double ym, double yc, double yp, const double* p, int j, int n) {\n";
+    f += "    (void)t; (void)ym; (void)yc; (void)yp; (void)p; (void)j; (void)n;\n";
+  }
+  f += rhs_body;
+  f += "\n  }\n";
+  if (Q > 0) {
+    f += "  NI_DEV static void aux(double t, const double* y, int n, const double* p, double* aux) {\n";
+    f += "    (void)t; (void)y; (void)n; (void)p; (void)aux;\n";
+    f += aux_body;
+    f += "\n  }\n";
+  }
+  f += "};\n";
+  return f;
+}
+
+NI_API int ni_module_compile_large(int component, const char *rhs_body, const char *aux_body, int n, int P, int Q,
+                                   int method, int mode, const char *nvrtc_options, ni_module **out) {
   if (!out) return fail(NI_ERR_INVALID, "out is NULL");
   *out = nullptr;
-  if (!stencil_body) return fail(NI_ERR_INVALID, "stencil_body is NULL");
-  std::string fsrc;
-  fsrc += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P < 0 ? 0 : P) + ", Q = 0;\n";
-  fsrc += "  static constexpr bool COMPONENT = false;\n  template <bool FAST>\n";
-  fsrc += "  NI_DEV static double eval(double t, double ym, double yc, double yp, const double* p, int j, int n) {\n";
-  fsrc += "    (void)t; (void)ym; (void)yc; (void)yp; (void)p; (void)j; (void)n;\n";
-  fsrc += stencil_body;
-  fsrc += "\n  }\n};\n";
-  return compile_stencil_module(fsrc, n, P, method, mode, nvrtc_options, out);
+  if (!rhs_body) return fail(NI_ERR_INVALID, "rhs_body is NULL");
+  if (Q < 0 || (Q > 0 && !aux_body)) return fail(NI_ERR_INVALID, "Q auxiliary outputs need an aux_body");
+  return compile_stencil_module(large_functor_src(component, rhs_body, aux_body, P, Q), n, P, Q, method, mode, nvrtc_options,
+                                out, component != 0);
+}
+
+NI_API int ni_module_compile_stencil(const char *stencil_body, int n, int P, int method, int mode,
+                                     const char *nvrtc_options, ni_module **out) {
+  return ni_module_compile_large(0, stencil_body, nullptr, n, P, 0, method, mode, nvrtc_options, out);
 }
 
 NI_API int ni_module_compile_component(const char *component_body, int n, int P, int method, int mode,
                                        const char *nvrtc_options, ni_module **out) {
-  if (!out) return fail(NI_ERR_INVALID, "out is NULL");
-  *out = nullptr;
-  if (!component_body) return fail(NI_ERR_INVALID, "component_body is NULL");
-  std::string fsrc;
-  fsrc += "struct NiUserStencil {\n  static constexpr int P = " + std::to_string(P < 0 ? 0 : P) + ", Q = 0;\n";
-  fsrc += "  static constexpr bool COMPONENT = true;\n  template <bool FAST>\n";
-  fsrc += "  NI_DEV static double eval(double t, const double* y, int j, int n, const double* p) {\n";
-  fsrc += "    (void)t; (void)y; (void)j; (void)n; (void)p;\n";
-  fsrc += component_body;
-  fsrc += "\n  }\n};\n";
-  return compile_stencil_module(fsrc, n, P, method, mode, nvrtc_options, out, true);
+  return ni_module_compile_large(1, component_body, nullptr, n, P, 0, method, mode, nvrtc_options, out);
 }
 
 NI_API int ni_module_info(const ni_module *m, int *n, int *P, int *Q, int *method, int *advanced, int *n_stages) {
@@ -502,6 +524,7 @@ struct ni_ensemble {
   double *y0_rows = nullptr, *t0_d = nullptr, *tb0_d = nullptr, *params_rows = nullptr;
   double *tb_saved = nullptr;
   double *max_step_d = nullptr, *first_step_d = nullptr;  // per-trajectory step limits (allocated on first use)
+  std::vector<double> tol_host;  // CTA-per-trajectory kernels: the rtol | atol vectors last copied to tol_d
   unsigned char *flag_d = nullptr;
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -794,9 +817,19 @@ NI_API int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *a
     e->a.tol_uniform = uni ? 1 : 0;
     e->a.rtol[0] = rtol[0];
     e->a.atol[0] = atol[0];
-    CU(cudaMemcpyAsync(e->mod.large.tol_d, rtol, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->mod.large.tol_d + n, atol, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaStreamSynchronize(e->stream));  // rtol / atol are caller-owned host buffers
+    // rtol / atol are caller-owned: copy them through an ensemble-owned staging vector, and only when they changed
+    // (a stream synchronise here cost the double-buffered end-to-end loop of C5 7 %)
+    bool same = e->tol_host.size() == 2 * (size_t)n;
+    for (int i = 0; same && i < n; ++i) same = e->tol_host[i] == rtol[i] && e->tol_host[n + i] == atol[i];
+    if (!same) {
+      CU(cudaStreamSynchronize(e->stream));  // an earlier copy may still read the staging vector
+      e->tol_host.assign(2 * (size_t)n, 0.0);
+      for (int i = 0; i < n; ++i) {
+        e->tol_host[i] = rtol[i];
+        e->tol_host[n + i] = atol[i];
+      }
+      CU(cudaMemcpyAsync(e->mod.large.tol_d, e->tol_host.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, e->stream));
+    }
   }
   e->a.max_step = max_step;
   e->a.first_step = first_step;
@@ -968,6 +1001,26 @@ NI_API int ni_ensemble_run_async(ni_ensemble *e) {
   return launch_run(e, 1ll << 62, true);
 }
 
+// Outcome of the most recent run / run_async / step: synchronises, then reports what the launch(es) left behind.
+NI_API int ni_ensemble_poll(ni_ensemble *e, int64_t *n_unfinished, int64_t *n_failed) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  unsigned long long all[8 * NI_PASSES];
+  CU(cudaMemcpyAsync(all, e->queue_all, sizeof all, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  unsigned long long flags = 0, unfinished = 0, failed = 0;
+  for (int k = 0; k < e->last_passes; ++k) {
+    flags |= all[8 * k + 1];
+    unfinished += all[8 * k + 2];
+    failed += all[8 * k + 5];
+  }
+  if (n_unfinished) *n_unfinished = (int64_t)unfinished;
+  if (n_failed) *n_failed = (int64_t)failed;
+  if (flags & NI_FLAG_REC_OVERFLOW)
+    return fail(NI_ERR_REC_OVERFLOW, "record log full (%lld records): drain it and run again", (long long)e->a.rec_cap);
+  return NI_OK;
+}
+
 NI_API int ni_ensemble_run(ni_ensemble *e, int64_t *n_unfinished) {
   if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
   CU(cudaSetDevice(e->device));
@@ -1075,7 +1128,6 @@ NI_API int ni_ensemble_ff2cond(ni_ensemble *e, int cond_kind, int index, double 
   if (cond_kind < NI_COND_Y_GT || cond_kind > NI_COND_AUX_LT) return fail(NI_ERR_INVALID, "unknown predicate kind %d", cond_kind);
   const int lim = cond_kind <= NI_COND_Y_LT ? e->mod.n : e->mod.Q;
   if (index < 0 || index >= lim) return fail(NI_ERR_INVALID, "predicate index %d out of range [0, %d)", index, lim);
-  if (e->mod.kind != NI_KIND_SMALL) return fail(NI_ERR_UNSUPPORTED, "ff2cond is implemented for the thread-per-trajectory kernels only");
   const bool on_y = cond_kind <= NI_COND_Y_LT, gt = cond_kind == NI_COND_Y_GT || cond_kind == NI_COND_AUX_GT;
   const std::string body = std::string("  return ") + (on_y ? "y[" : "aux[") + std::to_string(index) + "] " + (gt ? ">" : "<") + " cp[0];";
   return ni_ensemble_ff2cond_user(e, body.c_str(), &value, 1, hit, n_hit);
@@ -1088,8 +1140,7 @@ NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const
                                     uint8_t *hit, int64_t *n_hit) {
   if (!e || !cond_body) return fail(NI_ERR_INVALID, "ensemble / cond_body is NULL");
   if (n_params < 0 || n_params > 8 || (n_params > 0 && !cond_params)) return fail(NI_ERR_INVALID, "a predicate takes 0..8 parameters");
-  if (e->mod.kind != NI_KIND_SMALL || e->mod.rhs_src.empty())
-    return fail(NI_ERR_UNSUPPORTED, "user predicates are implemented for the thread-per-trajectory kernels only");
+  if (e->mod.rhs_src.empty()) return fail(NI_ERR_UNSUPPORTED, "this module does not carry the source of its right-hand side");
   CU(cudaSetDevice(e->device));
   // run kernels with a predicate compiled in, shared by every ensemble of the process (key: generated source +
   // options); never unloaded -- a few hundred KB per distinct (RHS, method, predicate)
@@ -1111,6 +1162,12 @@ NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const
     src += "extern \"C\" __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS(NiUserRhs::N)) ni_user_run_rec(const NiArgs a) { "
            "ni_small_run_body<NiUserRhs, " + M + ", " + A + ", true, " + F + ">(a); }\n";
     const std::string opts = m.fast ? "--fmad=true" : "--fmad=false";
+    std::string cond_src;
+    if (m.kind == NI_KIND_LARGE) {  // CTA-per-trajectory: the same templates as the ensemble's module + the predicate
+      cond_src = "__device__ __forceinline__ bool ni_user_cond(double t, const double* y, const double* aux, const double* cp) {\n"
+                 "  (void)t; (void)y; (void)aux; (void)cp;\n" + std::string(cond_body) + "\n}\n";
+      src = "large n=" + std::to_string(m.n) + " " + M + A + F + (m.component ? "c" : "s") + "\n" + m.rhs_src + cond_src;
+    }
     const std::string key = opts + "\n" + src;
     std::lock_guard<std::mutex> lock(cond_mu);
     for (auto &c : cond_cache)
@@ -1119,12 +1176,24 @@ NI_API int ni_ensemble_ff2cond_user(ni_ensemble *e, const char *cond_body, const
         ck = &found;
       }
     if (!ck) {
-      ni_module tmp;
-      const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
-      if (int rc = compile_and_load(src, opts.c_str(), names, &tmp)) return rc;
-      found.lib = tmp.lib;
-      found.k_run[0] = tmp.k_run[0];
-      found.k_run[1] = tmp.k_run[1];
+      if (m.kind == NI_KIND_LARGE) {
+        ni_module *tmp = nullptr;
+        const int mode = (m.advanced ? NI_MODE_ADVANCED : 0) | (m.fast ? NI_MODE_FAST : 0) | (m.scipy ? NI_MODE_SCIPY : 0);
+        if (int rc = compile_stencil_module(m.rhs_src, m.n, m.P, m.Q, m.method, mode, nullptr, &tmp, m.component, cond_src)) return rc;
+        found.lib = tmp->lib;
+        found.k_run[0] = tmp->k_run[0];
+        found.k_run[1] = tmp->k_run[1];
+        for (const void *k : {tmp->k_run[0], tmp->k_run[1]}) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
+        tmp->lib = nullptr;  // the kernels stay loaded for the process (cond_cache)
+        delete tmp;
+      } else {
+        ni_module tmp;
+        const char *names[3] = {"ni_user_init", "ni_user_run", "ni_user_run_rec"};
+        if (int rc = compile_and_load(src, opts.c_str(), names, &tmp)) return rc;
+        found.lib = tmp.lib;
+        found.k_run[0] = tmp.k_run[0];
+        found.k_run[1] = tmp.k_run[1];
+      }
       cond_cache.emplace_back(key, found);
       ck = &found;
     }
@@ -1278,6 +1347,22 @@ NI_API int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity) {
   if (capacity > a.rec_cap) {
     const size_t c = (size_t)capacity;
     int rc = NI_OK;
+    if (a.rec_cap > 0 || a.rec_traj) {  // growing: the old log goes (undrained records with it, as documented)
+      CU(cudaStreamSynchronize(e->stream));
+      void *old[] = {a.rec_traj, a.rec_step, a.rec_t, a.rec_y, a.rec_aux};
+      for (void *q : old) {
+        if (!q) continue;
+        for (size_t k = 0; k < e->allocs.size(); ++k)
+          if (e->allocs[k] == q) {
+            e->allocs.erase(e->allocs.begin() + (long)k);
+            break;
+          }
+        cudaFree(q);
+      }
+      a.rec_traj = a.rec_step = nullptr;
+      a.rec_t = a.rec_y = a.rec_aux = nullptr;
+      a.rec_cap = 0;
+    }
     if (rc == NI_OK) rc = dalloc(e, &a.rec_traj, c);
     if (rc == NI_OK) rc = dalloc(e, &a.rec_step, c);
     if (rc == NI_OK) rc = dalloc(e, &a.rec_t, c);

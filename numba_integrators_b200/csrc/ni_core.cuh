@@ -89,7 +89,7 @@ struct NiArgs {
   int compat;                   // 0: the reference's step semantics; 1: scipy.integrate semantics
   unsigned char *step_rejected; // compat == 1: "a rejection happened in the current step" (scipy's step_rejected)
   unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted,
-                                // [4] #trajectories parked for the next compaction pass
+                                // [4] #trajectories parked for the next compaction pass, [5] #retired FAILED / NONFINITE
   // compaction of the tail: once the queue is empty a warp with fewer than `park_below` busy
   // lanes parks its trajectories (state written back, index appended to `park_list`) and leaves; the next pass runs
   // the parked trajectories of all warps in full warps: its work items are `work_list[0 .. *work_count)`.
@@ -666,6 +666,7 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
           } else if (status == NI_ST_RUNNING && !parked) {
             atomicAdd(a.queue + 2, 1ull);
           }
+          if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
           if (last_accept) atomicAdd(a.queue + 3, 1ull);
           active = false;
         }
@@ -1009,6 +1010,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         a.n_rej[idx] += n_attempts - nacc;
         a.running[idx] = 0;
         if (parking) a.park_list[atomicAdd(a.queue + 4, 1ull)] = (unsigned int)idx;
+        if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
         active = false;
   };
 

@@ -215,6 +215,37 @@ NI_DEV NiLargeCtx ni_large_ctx(const NiArgs &a, double *smem, int cpt, int total
   return c;
 }
 
+// The state vector staged contiguously in shared memory, for the two consumers that see a CTA-per-trajectory system as
+// a whole: the auxiliary function (_advanced.py:181: the second return value of the right-hand side at the committed
+// state) and the ff2cond predicate (_API.py:41-49).  Both are user code over (t, y[0..n), p), evaluated by thread 0.
+// The stage slots are dead between two attempts, so the vector borrows them (n <= T * CPT doubles always fit one slot).
+template <class Rhs, int CPT>
+NI_DEV const double *ni_large_stage(NiLargeCtx &c, const double (&y)[CPT]) {
+  double *dst = Rhs::COMPONENT ? c.ys : c.vec;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int j = ni_large_j<Rhs>(c, i);
+    if (j < c.n) dst[j] = y[i];
+  }
+  __syncthreads();
+  return dst;
+}
+// auxiliary output of trajectory idx at (t, y) -> a.aux[idx][0..Q)
+template <class Rhs, int CPT>
+NI_DEV void ni_large_store_aux(const NiArgs &a, NiLargeCtx &c, long long idx, double t, const double (&y)[CPT],
+                               const double *p) {
+  if constexpr (Rhs::Q > 0) {
+    const double *ys = ni_large_stage<Rhs, CPT>(c, y);
+    if (c.tid == 0) {
+      double aux[Rhs::Q];
+      Rhs::aux(t, ys, c.n, p, aux);
+#pragma unroll
+      for (int i = 0; i < Rhs::Q; ++i) a.aux[idx * Rhs::Q + i] = aux[i];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- init (RK.__init__ + select_initial_step)
 template <class Rhs, int METHOD, int CPT>
 NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
@@ -296,6 +327,7 @@ NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
       a.n_rej[idx] = 0;
       a.running[idx] = 1;
     }
+    ni_large_store_aux<Rhs, CPT>(a, c, idx, t0, y, p);  // the auxiliary output of the FSAL seed evaluation
     __syncthreads();  // edge / partial buffers are reused by the next trajectory
   }
 }
@@ -332,6 +364,10 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       if (tid == 0) a.running[idx] = 0;
       continue;
     }
+#if NI_COND
+    if (a.cond_hit[idx]) continue;  // ff2cond: already stopped at its predicate
+#endif
+    bool parked = false;  // stopped by the ff2cond predicate: still RUNNING, but not "unfinished"
     double t = a.t[idx], h_abs = a.h_abs[idx], step_h = a.step_size[idx];
     const double tb = a.t_bound[idx], dir = a.direction[idx], mxs = ni_max_step(a, idx);
     double y[CPT], k0[CPT], kr[NiLargeRegs<METHOD>::COUNT][CPT], p[P > 0 ? P : 1];
@@ -548,6 +584,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       }
       if (!park) srej = !ok;
       const bool accepted = ok && !park;
+      bool cond_hit = false;
       if (accepted) {
         ++nacc;
         --acc_left;
@@ -560,6 +597,28 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
             a.rec_step[slot] = (unsigned int)nacc;
             a.rec_t[slot] = t;
           }
+        }
+        if constexpr ((REC && Rhs::Q > 0) || NI_COND != 0) {
+          // the recorded auxiliary output / the predicate see the committed state as a whole (thread 0)
+          const double *ys = ni_large_stage<Rhs, CPT>(c, y);
+          if (tid == 0) {
+            double aux[Rhs::Q > 0 ? Rhs::Q : 1];
+            aux[0] = 0.0;
+            if constexpr (Rhs::Q > 0) {
+              Rhs::aux(t, ys, n, p, aux);
+              if (REC) {
+#pragma unroll
+                for (int i = 0; i < Rhs::Q; ++i) a.rec_aux[slot * Rhs::Q + i] = aux[i];
+              }
+            }
+#if NI_COND
+            c.bcast[2] = ni_user_cond(t, ys, aux, a.cond_params) ? 1 : 0;
+#endif
+          }
+#if NI_COND
+          __syncthreads();
+          cond_hit = c.bcast[2] != 0;
+#endif
         }
       } else if (!park) {
         ++nrej;
@@ -575,6 +634,11 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       done = park || fail || nan;  // (separate statements: see the nvcc note in ni_small_run_body)
       if (att_left <= 0) done = true;
       if (accepted && acc_left <= 0) done = true;
+      if (cond_hit) {  // ff2cond: the trajectory stops here (_API.py:45-49)
+        if (tid == 0) a.cond_hit[idx] = 1;
+        parked = true;
+        done = true;
+      }
       if (accepted && !done && __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {
         step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);  // terminal step() of `while step(): pass`
         status = NI_ST_FINISHED;
@@ -591,6 +655,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         a.klast[idx * n + j] = k0[i];
       }
     }
+    ni_large_store_aux<Rhs, CPT>(a, c, idx, t, y, p);  // (_advanced.py:181: the auxiliary output at the committed state)
     if (tid == 0) {
       a.t[idx] = t;
       a.h_abs[idx] = h_abs;
@@ -600,7 +665,8 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       a.n_rej[idx] = nrej;
       a.running[idx] = last_accept ? 1 : 0;
       if (SP) a.step_rejected[idx] = srej ? 1 : 0;
-      if (status == NI_ST_RUNNING) atomicAdd(a.queue + 2, 1ull);
+      if (status == NI_ST_RUNNING && !parked) atomicAdd(a.queue + 2, 1ull);
+      if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
       if (last_accept) atomicAdd(a.queue + 3, 1ull);
     }
   }

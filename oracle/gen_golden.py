@@ -110,8 +110,24 @@ def f_readme_adv(t, y, p):
     return np.array((a + q[1], -y[0] + q[2])), np.array((a,))
 
 
+@nb.njit
+def f_heat_aux(t, y, p):
+    """heat1d with an auxiliary output over the whole state: (sum of y in index order, the middle component)"""
+    p[1][0] += 1
+    k = p[0][0]
+    n = y.size
+    dy = np.empty(n)
+    tot = 0.0
+    for j in range(n):
+        ym = y[j - 1] if j > 0 else 0.0
+        yp = y[j + 1] if j + 1 < n else 0.0
+        dy[j] = k * ((ym - 2.0 * y[j]) + yp)
+        tot += y[j]
+    return dy, np.array((tot, y[n // 2]))
+
+
 ADV_RHS = {'harmonic': f_harmonic, 'lorenz63': f_lorenz, 'vanderpol': f_vdp, 'heat1d': f_heat,
-           'burgers1d': f_burgers, 'exponential': f_exponential, 'riccati': f_riccati, 'blowup': f_blowup,
+           'heat1d_aux': f_heat_aux, 'burgers1d': f_burgers, 'exponential': f_exponential, 'riccati': f_riccati, 'blowup': f_blowup,
            'readme_advanced': f_readme_adv}
 
 # ---- basic-form RHS (no parameters) for the basic-vs-Advanced identity cases ---------------
@@ -261,6 +277,52 @@ def run_basic_case(name, rhs, method, t0, y0, t_bound, rtol, atol, max_step=np.i
     print(f'{name:34s} basic, {k} steps, t={s.t!r}')
 
 
+def _make_cond_runner(direct):
+    @nb.njit
+    def run(fun, t0, y0, p, t_bound, rtol, atol, j, thr):
+        """ni.ff2cond (_API.py:41-49) with the predicate y[j] < thr: step until it holds after an accepted step"""
+        cnt = np.zeros(1, np.int64)
+        s = direct(fun, t0, y0.copy(), (p.copy(), cnt), t_bound, np.inf, rtol, atol, 0.0)
+        k = 0
+        hit = False
+        while s.step():
+            k += 1
+            if s.y[j] < thr:
+                hit = True
+                break
+        return s.t, s.y, s.auxiliary, s.h_abs, k, cnt[0], hit
+    return run
+
+
+COND_RUN = {m: _make_cond_runner(d) for m, d in DIRECT.items()}
+
+
+def run_cond_case(name, rhs, method, t0, y0, params, t_bound, rtol, atol, j, thr, note=''):
+    """ff2cond(solver, lambda s, thr: s.y[j] < thr, thr) on every row through the reference's Advanced solver."""
+    if not _wanted(name):
+        return
+    y0 = np.atleast_2d(np.asarray(y0, np.float64))
+    N, n = y0.shape
+    params = np.asarray(params, np.float64).reshape(N, -1)
+    rt = np.broadcast_to(np.asarray(rtol, np.float64), (n,)).copy()
+    at = np.broadcast_to(np.asarray(atol, np.float64), (n,)).copy()
+    o = dict(t=np.empty(N), y=np.empty((N, n)), h_abs=np.empty(N), n_accepted=np.zeros(N, np.int64),
+             n_rejected=np.zeros(N, np.int64), hit=np.zeros(N, np.uint8))
+    aux = []
+    for i in range(N):
+        t, y, a, h_abs, k, nfev, hit = COND_RUN[method](ADV_RHS[rhs], float(t0), y0[i], params[i], float(t_bound), rt, at,
+                                                        int(j), float(thr))
+        o['t'][i], o['y'][i], o['h_abs'][i], o['n_accepted'][i], o['hit'][i] = t, y, h_abs, k, hit
+        o['n_rejected'][i] = (nfev - 2) // S_PRIME[method] - k
+        aux.append(a)
+    meta = dict(name=name, rhs=rhs, method=method, advanced=True, max_step=float('inf'), first_step=0.0,
+                cond_index=int(j), cond_threshold=float(thr), note=note)
+    np.savez_compressed(OUT / f'{name}.npz', meta=json.dumps(meta), t0=np.full(N, float(t0)), y0=y0, params=params,
+                        t_bound=np.full(N, float(t_bound)), rtol=rt, atol=at, aux=np.array(aux),
+                        rec_t=np.zeros((0, 0)), **o)
+    print(f'{name:34s} N={N:4d} n={n:5d} acc={o["n_accepted"].mean():9.1f} hit={o["hit"].mean():.2f}')
+
+
 def main():
     # -- C1: README example (README.md:47-69), basic API, every step recorded
     run_basic_case('c1_readme_sine_rk45', 'harmonic', 'RK45', 0.0, [0.0, 1.0], 1.0, 1e-8, 1e-8)
@@ -334,6 +396,11 @@ def main():
     run_case('per_traj_limits_lorenz_rk45', w.rhs, 'RK45', 0.0, w.y0, w.params, 1.0, 1e-8, 1e-8,
              max_step=[np.inf, 0.02, 0.005, np.inf, 0.011, 1.0, 0.0025, np.inf],
              first_step=[0.0, 0.0, 1e-3, 1e-4, 0.0, 5e-3, 0.0, 2e-2], rec_cap=128, rec_traj=8)
+    # -- CTA-per-trajectory systems with an auxiliary output over the whole state, and ff2cond on them
+    w = wl.c5_heat(N=4, n=48, t_bound=0.3)
+    run_case('heat48_aux_rk45', 'heat1d_aux', 'RK45', 0.0, w.y0, w.params, 0.3, 1e-8, 1e-8, rec_cap=32, rec_traj=1)
+    run_cond_case('heat48_aux_ff2cond_rk45', 'heat1d_aux', 'RK45', 0.0, w.y0, w.params, 5.0, 1e-8, 1e-8, j=24, thr=0.05,
+                  note='ni.ff2cond(solver, lambda s, thr: s.y[24] < thr, 0.05)')
     w = wl.c5_heat(N=4, n=48, t_bound=0.3)
     run_case('per_traj_limits_heat48_rk23', 'heat1d', 'RK23', 0.0, w.y0, w.params, 0.3, 1e-6, 1e-8,
              max_step=[np.inf, 2e-3, 5e-4, np.inf], first_step=[0.0, 1e-4, 0.0, 1e-5])

@@ -46,6 +46,7 @@ enum {
   NI_RHS_RICCATI = 6,     /* y' = 2y/x - x^2 y^2   (reference.py:38) */
   NI_RHS_README_ADV = 7,  /* README.md:80-85: p=(a,b0,b1): aux=a*y1; dy=(aux+b0, -y0+b1) */
   NI_RHS_BLOWUP = 8,      /* y' = y^2 (failure-exit fixture) */
+  NI_RHS_HEAT1D_AUX = 9,  /* heat1d with aux = (sum_j y_j in index order, y[n/2]): oracle/gen_golden.py f_heat_aux */
   NI_RHS_COUNT
 };
 enum { NI_ST_RUNNING = 0, NI_ST_FINISHED = 1, NI_ST_FAILED = 2, NI_ST_NONFINITE = 3 };
@@ -98,11 +99,19 @@ static void rhs_eval(const ni_oracle_solver *s, double t, const double *y, doubl
     dy[1] = (p[0] * (1.0 - y[0] * y[0])) * y[1] - y[0];
     break;
   case NI_RHS_HEAT1D:
+  case NI_RHS_HEAT1D_AUX: {
+    double tot = 0.0;
     for (int j = 0; j < n; ++j) {
       const double ym = j > 0 ? y[j - 1] : 0.0, yp = j + 1 < n ? y[j + 1] : 0.0;
       dy[j] = p[0] * ((ym - 2.0 * y[j]) + yp);
+      tot += y[j];
+    }
+    if (aux && s->Q > 1) {
+      aux[0] = tot;
+      aux[1] = y[n / 2];
     }
     break;
+  }
   case NI_RHS_BURGERS1D:
     for (int j = 0; j < n; ++j) {
       const double ym = j > 0 ? y[j - 1] : 0.0, yp = j + 1 < n ? y[j + 1] : 0.0;

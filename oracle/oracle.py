@@ -25,9 +25,9 @@ _LIB_PATH = _HERE / 'libni_oracle.so'
 
 RK23, RK45 = 0, 1
 RHS_IDS = {'harmonic': 0, 'sine': 0, 'lorenz63': 1, 'vanderpol': 2, 'heat1d': 3, 'burgers1d': 4,
-           'exponential': 5, 'riccati': 6, 'readme_advanced': 7, 'blowup': 8}
+           'exponential': 5, 'riccati': 6, 'readme_advanced': 7, 'blowup': 8, 'heat1d_aux': 9}
 # (P, Q) of each built-in
-RHS_PQ = {0: (0, 0), 1: (3, 1), 2: (1, 0), 3: (1, 0), 4: (2, 0), 5: (0, 0), 6: (0, 0), 7: (3, 1), 8: (0, 0)}
+RHS_PQ = {0: (0, 0), 1: (3, 1), 2: (1, 0), 3: (1, 0), 4: (2, 0), 5: (0, 0), 6: (0, 0), 7: (3, 1), 8: (0, 0), 9: (1, 2)}
 ST_RUNNING, ST_FINISHED, ST_FAILED, ST_NONFINITE = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)

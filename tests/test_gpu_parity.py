@@ -29,7 +29,9 @@ TOL = {
     'failure_blowup_rk45_basic': (1e-9, 1.0),
 }
 DEFAULT_TOL = (1e-12, 0.999)
-FULL_RUN = [n for n in golden_names() if load_golden(n)[0].get('n_steps', 10 ** 9) >= 10 ** 6]
+# (fixtures of user-snippet right-hand sides and of ff2cond have their own tests: test_gpu_large_features.py)
+GENERIC = [n for n in golden_names() if load_golden(n)[0]['rhs'] in ni.rhs._BUILTIN_IDS and 'cond_index' not in load_golden(n)[0]]
+FULL_RUN = [n for n in GENERIC if load_golden(n)[0].get('n_steps', 10 ** 9) >= 10 ** 6]
 
 
 def build(meta, g, rows=slice(None), **kw):
@@ -80,7 +82,7 @@ STREAM_TOL = {}  # name -> (tol_t, tol_y); none needed: on B200 the worst |dt| i
 STREAM_DEFAULT = (1e-9, 1e-10)  # |dt| <= 1e-9 max(1, |t|);  |dy - f dt| <= 1e-10 max(1, |y|)
 
 
-@pytest.mark.parametrize('name', [n for n in golden_names() if load_golden(n)[1]['rec_t'].size])
+@pytest.mark.parametrize('name', [n for n in GENERIC if load_golden(n)[1]['rec_t'].size])
 def test_lock_step_sequence_matches_reference(name, oracle):
     """ni.step() by ni.step(): every accepted (t, y) against the reference's recorded sequence."""
     meta, g = load_golden(name)
