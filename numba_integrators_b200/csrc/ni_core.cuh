@@ -910,16 +910,42 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
 
 // ---------------------------------------------------------------- run kernel, lean variant: cold block
 // Cold block of the lean run body: the attempt of this lane needs one of the rarely needed pieces of the controller --
-// the NaN latch (the reference would spin forever: status NONFINITE) or the step-size floor of the failure exit
-// (_basic.py:179-180) -- recomputed with the general formulas of ni_small_run_impl.  Out of line and
-// by value, so that the hot loop pays one predicated branch for it.  flags in: 1 = accepted, 2 = error norm is NaN;
-// out: 1 = accepted, 4 = failure exit (commit the rejected t, y), 8 = leave with `status`.
+// operands outside the guarded division / root ranges (the tail again, with the operators), the NaN latch (the
+// reference would spin forever: status NONFINITE) or the step-size floor of the failure exit (_basic.py:179-180) --
+// recomputed with the general formulas of ni_small_run_impl.  Out of line and by value, so that the hot loop pays one
+// predicated branch for it and keeps its flags in predicate registers.
+// flags out: 1 = accepted, 4 = failure exit (commit the rejected t, y), 8 = leave with `status`.
 struct NiLeanCold {
   double h_new;
   int flags, status;
 };
-static __device__ __noinline__ NiLeanCold ni_lean_cold(double t, double dir, double h_abs, double pw, int flags) {
-  const bool ok = (flags & 1) != 0, nan = (flags & 2) != 0;
+template <int n>
+struct NiLeanColdIn {
+  double num[n], y[n], yn[n];
+};
+template <int n, int METHOD, bool FAST>
+static __device__ __noinline__ NiLeanCold ni_lean_cold(NiLeanColdIn<n> v, const double *rtol, const double *atol, double t,
+                                                       double dir, double h_abs, double en, double pw, int ok_in, unsigned out) {
+  using Tab = NiTab<METHOD>;
+  bool ok = ok_in != 0, nan = false;
+  if constexpr (FAST) {
+    if (out != 0u) {  // (en holds the mean square error) outside [2^-100, 2^100) or NaN: the saturating root
+      pw = ni_pow_fast<2 * (Tab::ORDER + 1)>(en);
+      ok = en < 1.0;
+      nan = en != en;
+    }
+  } else {
+    if (out != 0u) {
+      double ev[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i)
+        ev[i] = v.num[i] / __dadd_rn(atol[i], __dmul_rn(fmax(fabs(v.y[i]), fabs(v.yn[i])), rtol[i]));
+      en = ni_rms<n>(ev);
+      pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
+      ok = en < 1.0;
+      nan = en != en;
+    }
+  }
   const double sp = __dmul_rn(0.9, pw);
   const double fac = fmax(0.2, fmin(10.0, sp));  // en == 0 saturates the power, i.e. MAX_FACTOR (:172)
   NiLeanCold r;
@@ -942,14 +968,14 @@ static __device__ __noinline__ NiLeanCold ni_lean_cold(double t, double dir, dou
 // register operand of every other instruction adds half a cycle).  The general body above spends ~160 such operands per
 // attempt on selects, 64-bit integer compares and counters.  Here everything that is not needed on the usual path
 // is moved to places that run rarely:
-//  * step entry (_basic.py:139-156: 8 ulp(t) floor, t + h, clip to t_bound) is evaluated EXACTLY in the service branch
-//    for a trajectory that is loaded, or whose last attempt raised one of two conservative integer tests -- "t + h may
-//    have reached t_bound" (a monotone key of the high word of t + h against the key of t_bound, 2 instructions) and
-//    "h_abs may be below 8 ulp(t)" (high word of h_abs against a power-of-two bound from the exponent of t, 1
-//    instruction); otherwise the entry is h = +-h_abs, tn = t + h, bit for bit what the exact entry computes when
-//    neither clamp applies;
-//  * the failure exit (:179-180) and the NaN latch live in an out-of-line cold block behind the second conservative
-//    test;
+//  * step entry (_basic.py:139-156: 8 ulp(t) floor, t + h, clip to t_bound) is evaluated EXACTLY only where it can
+//    matter, found by two conservative integer tests: "t + h may have reached t_bound" (a monotone key of the high word
+//    of t + h against the key of t_bound, 2 instructions; the lane then takes a short rare block with the exact clip)
+//    and "h_abs may be below 8 ulp(t)" (high word of h_abs against a power-of-two bound from the exponents of t and
+//    t_bound, 1 instruction; the lane then takes the cold block and the exact entry of the service branch); otherwise
+//    the entry is h = +-h_abs, tn = t + h, bit for bit what the exact entry computes when neither clamp applies;
+//  * the failure exit (:179-180), the NaN latch and operands outside the guarded division / root ranges share ONE
+//    out-of-line cold block behind the second conservative test; a lane that takes it commits its attempt there;
 //  * attempts are counted by a warp-uniform iteration counter (rejected = iterations in residency - accepted), status /
 //    step_size / running are derived at retirement, lanes without work are not masked: they run on benign values and
 //    cannot raise a flag.
@@ -969,10 +995,10 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
   for (int i = 0; i < n; ++i) y[i] = kl[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < (P > 0 ? P : 1); ++i) p[i] = 0.0;
-  int status = NI_ST_RUNNING, nacc = 0;
+  int status = NI_ST_RUNNING, nacc = 0, acc0 = 0, rej0 = 0;
   unsigned iter = 0, it0 = 0;  // hot-loop passes of this warp; the pass count at which the lane's trajectory was loaded
   int kx = 0, tbk = 0x7fffffff;  // reach key: (hi(tn) ^ kx) >= tbk  <=  direction * (tn - t_bound) >= 0
-  int xs = 0;                    // hi(h_abs) <u xs  <=  h_abs may be below 8 ulp(t) of this or the next step
+  int xs = 0;                    // hi(h_abs) <u xs  <=  h_abs may be below 8 ulp(t) somewhere between t and t_bound
 
   const long long n_work = a.work_list ? (long long)*a.work_count : N;
   // write the lane's trajectory back: it has finished / failed, or (`parking`) it moves to the next compaction pass
@@ -1006,8 +1032,8 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
           }
         }
         a.status[idx] = status;
-        a.n_acc[idx] += nacc;
-        a.n_rej[idx] += n_attempts - nacc;
+        a.n_acc[idx] = acc0 + nacc;  // (acc0 / rej0: the counters as loaded, so that the retire path only stores)
+        a.n_rej[idx] = rej0 + n_attempts - nacc;
         a.running[idx] = 0;
         if (parking) a.park_list[atomicAdd(a.queue + 4, 1ull)] = (unsigned int)idx;
         if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
@@ -1033,22 +1059,16 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
           break;
         }
         if (a.work_list) idx = a.work_list[idx];
+        // every load of the trajectory is issued before the first one is needed: one memory round trip per refill
+        // (a fast-forward run almost never pops a trajectory that is not RUNNING)
         status = a.status[idx];
-        if (status != NI_ST_RUNNING) {
-          a.running[idx] = 0;  // step() on a finished / failed solver returns False
-          continue;
-        }
         t = a.t[idx];
         h_abs = a.h_abs[idx];
         tb = a.t_bound[idx];
         dir = a.direction[idx];
-        if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached (_basic.py:135-136)
-          a.step_size[idx] = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
-          a.status[idx] = NI_ST_FINISHED;
-          a.running[idx] = 0;
-          continue;
-        }
         step_h = a.step_size[idx];
+        acc0 = a.n_acc[idx];
+        rej0 = a.n_rej[idx];
 #pragma unroll
         for (int i = 0; i < n; ++i) {
           y[i] = a.y[i * N + idx];
@@ -1056,6 +1076,16 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
+        if (status != NI_ST_RUNNING) {
+          a.running[idx] = 0;  // step() on a finished / failed solver returns False
+          continue;
+        }
+        if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached (_basic.py:135-136)
+          a.step_size[idx] = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
+          a.status[idx] = NI_ST_FINISHED;
+          a.running[idx] = 0;
+          continue;
+        }
         // reach key of this trajectory: hi(tn) ^ kx is monotone in dir * tn over the sign regime in which t_bound can
         // be reached, and compares as "reached" outside it
         const int tbh = __double2hiint(tb);
@@ -1065,6 +1095,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
           kx = tbh < 0 ? (int)0x80000000 : -1;
         }
         tbk = tbh ^ kx;
+        // step-size floor test of this residency: t moves from here towards t_bound, so the larger of the two
+        // exponents bounds 8 ulp(t) for every attempt (64 ulp of the larger magnitude: conservative by 8x or more)
+        const int ea = __double2hiint(t) & 0x7ff00000, eb = tbh & 0x7ff00000;
+        const int xe = (ea > eb ? ea : eb) - (46 << 20);
+        xs = xe > 0x00100000 ? xe : 0x00100000;
         nacc = 0;
         it0 = iter;
         active = true;
@@ -1095,8 +1130,6 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
           // (the clipped step t_bound - t has the sign of `direction`: h below is again +-h_abs)
           h_abs = fabs(__dadd_rn(tn, -t));
         }
-        const int xe = (__double2hiint(t) & 0x7ff00000) - (46 << 20);
-        xs = xe > 0x00100000 ? xe : 0x00100000;
       } else {
         // a lane without work keeps executing the arithmetic: give it values that raise no flag
         t = 0.0;
@@ -1119,27 +1152,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     bool ok;
     unsigned out;
     ni_rk_attempt<Rhs, METHOD, FAST>(a, t, tn, h, y, kl, p, yn, kn, auxn, num, en, pw, ok, out);
-    bool nan = false;
     if constexpr (FAST) {
-      // (en holds the mean square error) the root without its range checks; outside [2^-100, 2^100) or NaN: redone
+      // (en holds the mean square error) the root without its range checks; outside [2^-100, 2^100) or NaN: cold block
       pw = ni_pow_fast_core<2 * (Tab::ORDER + 1)>(en);
       ok = (unsigned)__double2hiint(en) < 0x3ff00000u;
-      if (active && (unsigned)(__double2hiint(en) - 0x39b00000) >= (0x46300000u - 0x39b00000u)) {
-        pw = ni_pow_fast<2 * (Tab::ORDER + 1)>(en);
-        ok = en < 1.0;
-        nan = en != en;
-      }
-    } else {
-      if (active && out != 0u) {  // an operand outside the guarded ranges: the tail again, with the operators
-        double ev[n];
-#pragma unroll
-        for (int i = 0; i < n; ++i)
-          ev[i] = num[i] / __dadd_rn(a.atol[i], __dmul_rn(fmax(fabs(y[i]), fabs(yn[i])), a.rtol[i]));
-        en = ni_rms<n>(ev);
-        pw = ni_pow_ctrl<Tab::ORDER + 1>(en);
-        ok = en < 1.0;
-        nan = en != en;
-      }
+      out = (unsigned)(__double2hiint(en) - 0x39b00000) >= (0x46300000u - 0x39b00000u) ? 1u : 0u;
     }
     // ---- controller + commit (_basic.py:171-180)
     // SAFETY * en ** exp > 0 and never NaN here; both clamps unconditionally (an accepted attempt has factor > 0.9 >
@@ -1149,19 +1166,34 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     double fac = __double2hiint(sp) >= 0x40240000 ? 10.0 : sp;
     fac = ni_lt_pos(fac, 0.2) ? 0.2 : fac;
     double h_new = __dmul_rn(h_abs, fac);
-    bool fail = false, cold = false;
-    if (active && (nan || (unsigned)__double2hiint(h_new) < (unsigned)xs)) {
-      const NiLeanCold c = ni_lean_cold(t, dir, h_abs, pw, (ok ? 1 : 0) | (nan ? 2 : 0));
+    // Lanes that need the cold block commit there; the hot commit below runs on predicates that never leave the
+    // predicate registers (a flag merged across the cold call is materialised as a byte: six more instructions)
+    // (bitwise, not short-circuit: nvcc otherwise threads the `active` test through the clamps above and duplicates them)
+    const bool rare = active & ((out != 0u) | ((unsigned)__double2hiint(h_new) < (unsigned)xs));
+    bool cold = false;
+    if (rare) {
+      NiLeanColdIn<n> v;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        v.num[i] = num[i];
+        v.y[i] = y[i];
+        v.yn[i] = yn[i];
+      }
+      const NiLeanCold c = ni_lean_cold<n, METHOD, FAST>(v, a.rtol, a.atol, t, dir, h_abs, en, pw, ok ? 1 : 0, out);
       h_new = c.h_new;
-      ok = (c.flags & 1) != 0;
-      fail = (c.flags & 4) != 0;
+      if (c.flags & 5) {  // accepted, or the failure exit: commit the attempt (the rejected t, y when failing)
+        t = tn;
+#pragma unroll
+        for (int i = 0; i < n; ++i) y[i] = yn[i];
+      }
+      nacc += c.flags & 1;
       if (c.flags & 8) {
         status = c.status;
         step_h = h;  // step_size of the exit
       }
       cold = true;  // the coming step entry is evaluated exactly in the service branch (8 ulp floor)
     }
-    const bool take = ok || fail;
+    const bool take = ok && !rare;
     t = take ? tn : t;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
@@ -1169,17 +1201,31 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
       kl[i] = kn[i];  // also after a rejection: the stale FSAL stage
     }
     h_abs = h_new;
-    nacc += (int)ok;
+    if (take) ++nacc;
     ++iter;
-    // ---- fast step entry of the next attempt: exact unless one of the conservative tests sends the lane to the
-    // service branch.  A step that ended on t_bound raises the reach test by itself (t == t_bound now).
+    // ---- step entry of the next attempt (_basic.py:145-156): h = +-h_abs, tn = t + h; the clip to t_bound is evaluated
+    // exactly, but only by the lanes whose t + h may have reached t_bound (conservative key test: the last attempt of a
+    // trajectory, 0.2 % of the lane-attempts); the 8 ulp floor of a step entry (:139-143) is the service branch's, which
+    // the cold block requests.  A trajectory whose last step ended on t_bound asks for the service branch here.
     {
-      const int xe = (__double2hiint(t) & 0x7ff00000) - (46 << 20);
-      xs = xe > 0x00100000 ? xe : 0x00100000;
       const double hn = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
                             : h_abs;
       tn = __dadd_rn(t, hn);
-      svc = cold || (__double2hiint(tn) ^ kx) >= tbk;
+      svc = cold;
+      if ((__double2hiint(tn) ^ kx) >= tbk) {
+        if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // (:135) t_bound has been reached: the trajectory leaves
+          svc = true;
+        } else {
+          const double dtb = __dadd_rn(tn, -tb);
+          const bool zero = ((__double2hiint(dtb) << 1) | __double2loint(dtb)) == 0;
+          const bool same = (__double2hiint(dtb) ^ __double2hiint(dir)) >= 0;
+          if (zero || same) {  // direction * (t_new - t_bound) >= 0: the attempt ends on t_bound
+            tn = tb;
+            // (the clipped step t_bound - t has the sign of `direction`: the next h is again +-h_abs)
+            h_abs = fabs(__dadd_rn(tn, -t));
+          }
+        }
+      }
     }
   }
 }

@@ -4,7 +4,7 @@ The thread-per-trajectory run kernel is bound by register-file read bandwidth (D
 profiles/r02_issue_model.txt: a scheduler reads two 32-bit register operands per lane per cycle, and an FP64 instruction
 with two 64-bit register sources uses that for both of its pipe cycles).  This script prints, for one pass through the
 hot loop -- everything between the loop's EXIT test and its back edge, minus the cold regions (forward-skipped spans that
-contain a CALL: the operator slow paths, the lean body's cold block) -- D = FP64-pipe instructions, I = all others, and
+contain a CALL or an FP64 compare: the operator slow paths, the lean body's cold block and its rare clip to t_bound) -- D = FP64-pipe instructions, I = all others, and
 R = 32-bit register source operands read (64-bit operands count twice, operands served by the reuse cache not at all):
 one attempt costs about max(2 D, R / 2) scheduler cycles.  Every loop body of a kernel is listed (ni_small_run_body
 carries two: the lean one and the general one).
@@ -95,7 +95,9 @@ def hot_loops(obj, kernel):
             mm = re.match(r'@!?P\d BRA (?:P\d, )?0x([0-9a-f]+)$', t)
             if mm:
                 skipped = [b for b, u in body if a < b < int(mm.group(1), 16)]
-                if any('CALL' in u for b, u in body if b in skipped):
+                # cold: the operator slow paths and the lean body's cold block (a CALL), the rare exact clip to
+                # t_bound (the only FP64 compares of the loop)
+                if any('CALL' in u or u.startswith('DSETP') for b, u in body if b in skipped):
                     cold.update(skipped)
         hot = [(a, t) for a, t in body if a not in cold]
         hist = collections.Counter(_opcode(t) for a, t in hot)
