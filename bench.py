@@ -180,6 +180,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='CPU work budget of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--record', action='store_true', help='record every accepted step to the HBM log (always on for c2)')
     ap.add_argument('--no-fast', action='store_true', help='skip the extra fast-arithmetic launches (roofline.fast)')
     ap.add_argument('--arithmetic', default='strict', choices=['strict', 'fast'],
                     help="'strict' = the reference's unfused FP64 arithmetic (default, bit-faithful); 'fast' = opt-in mode")
@@ -213,7 +214,8 @@ def main():
     w = make_workload(args.workload, args.traj, rank, world, args.t_bound)
     N, n = w.N, w.n
     f = ni.BuiltinRHS(w.rhs)
-    record = args.workload == 'c2'
+    record = args.workload == 'c2' or args.record
+    rec_per_traj = {'c2': 1000, 'c3': 620, 'c4': 5200, 'c5': 260}[args.workload]  # accepted steps per trajectory, with headroom
 
     def build_ensemble(wk=None, arithmetic=None):
         wk = wk or w
@@ -225,7 +227,7 @@ def main():
             ctor = ni.RK45 if wk.method == 'RK45' else ni.RK23
             e = ctor(f(*wk.params.T) if f.P else f, wk.t0, wk.y0, wk.t_bound, **kw)
         if record:
-            e.record_enable(int(wk.N * 1000))  # the whole ensemble's accepted steps stay in HBM (~877 per trajectory)
+            e.record_enable(int(wk.N * rec_per_traj))  # the whole ensemble's accepted steps stay in HBM
         return e
 
     def timed_steps(e, steps, warmup):

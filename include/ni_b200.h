@@ -76,7 +76,7 @@ extern "C" {
 #define NI_F_COND_HIT 13  /* uint8[N]  ff2cond predicate hit                      */
 /* record log buffers (ni_ensemble_device_ptr only; capacity entries, see the recording section) */
 #define NI_F_REC_TRAJ 20  /* uint32[cap]                                          */
-#define NI_F_REC_STEP 21  /* uint32[cap]                                          */
+#define NI_F_REC_STEP 21  /* (not stored any more: NI_ERR_UNSUPPORTED; ni_ensemble_record_drain numbers the steps) */
 #define NI_F_REC_T 22     /* double[cap]                                          */
 #define NI_F_REC_Y 23     /* double [n][cap] (layout 0) or [cap][n] (layout 1)    */
 #define NI_F_REC_AUX 24   /* double [Q][cap] (layout 0) or [cap][Q] (layout 1)    */
@@ -215,10 +215,13 @@ int ni_ensemble_get_terminal(ni_ensemble *e, void *host_out);
 
 
 /* ---- recording of accepted steps into an HBM append log --------------------------------
- * (README.md:62-69 appends solver.t / solver.y after every accepted step.)  Records are
- * (trajectory, step index, t, y[n], aux[Q]); order within the log is arbitrary.  record_count gives the
- * number of log SLOTS in use (an upper bound: warps reserve slots in chunks); record_drain needs buffers for
- * that many records, drops the unused slots and returns the number of real records in *n_out. */
+ * (README.md:62-69 appends solver.t / solver.y after every accepted step.)  A record is (trajectory, t, y[n], aux[Q]):
+ * 8 (1 + n + Q) bytes of payload + a 4-byte trajectory tag.  The log stores no step numbers: the records of one
+ * trajectory appear in step order (slot order), interleaved with those of other trajectories.  record_count gives the
+ * number of log SLOTS in use (an upper bound: warps reserve slots in chunks); record_drain needs buffers for that many
+ * records, compacts the log on the device (window by window through a fixed staging buffer: unused slots dropped, order
+ * kept), numbers the steps (`step`, may be NULL: the k-th record of a trajectory in this batch is step
+ * n_accepted - records_in_batch + k) and returns the number of real records in *n_out. */
 int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity);
 int ni_ensemble_record_count(ni_ensemble *e, int64_t *count);
 int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, double *t, double *y, double *aux,

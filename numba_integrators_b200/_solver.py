@@ -433,9 +433,10 @@ class Ensemble:
 
     def record_views(self):
         """Zero-copy torch views of the HBM record log for device-side consumers: dict with `count` (slots in
-        use), traj, step (uint32 viewed as int32), t, y, aux.  Layout: y is [n][capacity] for the
-        thread-per-trajectory kernels, [capacity][n] for the CTA-per-trajectory ones; slots whose traj is -1
-        (0xffffffff) were reserved but not written."""
+        use), traj (uint32 viewed as int32), t, y, aux.  Layout: y is [n][capacity] for the thread-per-trajectory
+        kernels, [capacity][n] for the CTA-per-trajectory ones; slots whose traj is -1 (0xffffffff) were reserved but
+        not written.  The log stores no step numbers: the records of one trajectory appear in step order (slot order),
+        `record_drain()` numbers them."""
         import torch
         from .distributed import _DeviceView
         cap, count = self._rec_cap, self.record_count()
@@ -444,8 +445,7 @@ class Ensemble:
         def view(field, shape, ts):
             return torch.as_tensor(_DeviceView(self.device_pointer(field), shape, ts), device=dev)
         small = self.kind == 0
-        out = {'count': count, 'traj': view(_lib.F_REC_TRAJ, (cap,), '<i4'), 'step': view(_lib.F_REC_STEP, (cap,), '<i4'),
-               't': view(_lib.F_REC_T, (cap,), '<f8'),
+        out = {'count': count, 'traj': view(_lib.F_REC_TRAJ, (cap,), '<i4'), 't': view(_lib.F_REC_T, (cap,), '<f8'),
                'y': view(_lib.F_REC_Y, (self.n, cap) if small else (cap, self.n), '<f8')}
         if self.Q:
             out['aux'] = view(_lib.F_REC_AUX, (self.Q, cap) if small else (cap, self.Q), '<f8')

@@ -1061,11 +1061,84 @@ __global__ void ni_k_to_rows(const double *src, double *dst, long long N, int c)
     dst[k] = src[(long long)j * N + i];
   }
 }
-__global__ void ni_k_rec_rows(const double *src, double *dst, long long count, long long cap, int c) {
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < count * c; k += (long long)gridDim.x * blockDim.x) {
-    const long long i = k / c;
-    const int j = (int)(k - i * c);
-    dst[k] = src[(long long)j * cap + i];
+// ---- draining the record log: order-preserving compaction of a window of slots into row-major staging buffers
+// (slots reserved in chunks but never written carry NI_REC_INVALID).  Three small kernels per window: valid slots per
+// block of NI_DRAIN_BLOCK slots, exclusive scan of the block counts (one CTA), scatter.
+#define NI_DRAIN_BLOCK 4096
+__global__ void __launch_bounds__(256) ni_k_drain_count(const unsigned *rec_traj, long long s0, long long count, unsigned *block_count) {
+  __shared__ unsigned warp_sums[8];
+  const long long b0 = s0 + (long long)blockIdx.x * NI_DRAIN_BLOCK;
+  unsigned c = 0;
+  for (int k = threadIdx.x; k < NI_DRAIN_BLOCK; k += 256) {
+    const long long sl = b0 + k;
+    c += (sl < s0 + count && rec_traj[sl] != NI_REC_INVALID) ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+    for (int w = 0; w < 8; ++w) tot += warp_sums[w];
+    block_count[blockIdx.x] = tot;
+  }
+}
+__global__ void __launch_bounds__(1024) ni_k_drain_scan(unsigned *block_count, int nblocks, unsigned long long *total) {
+  // exclusive scan in place (nblocks <= a few thousand: one CTA, sequential over tiles of 1024)
+  __shared__ unsigned tile[1024];
+  __shared__ unsigned carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + (int)threadIdx.x;
+    const unsigned v = i < nblocks ? block_count[i] : 0u;
+    tile[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const unsigned add = threadIdx.x >= (unsigned)o ? tile[threadIdx.x - o] : 0u;
+      __syncthreads();
+      tile[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < nblocks) block_count[i] = carry + tile[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += tile[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+// small != 0: rec_y / rec_aux are component-major [c][cap]; else row-major [cap][c]
+__global__ void __launch_bounds__(256) ni_k_drain_pack(NiArgs a, int small, int n, int Q, long long s0, long long count,
+                                                       const unsigned *block_offset, unsigned *o_traj, double *o_t, double *o_y,
+                                                       double *o_aux) {
+  __shared__ unsigned warp_base[8];
+  __shared__ unsigned running;
+  if (threadIdx.x == 0) running = block_offset[blockIdx.x];
+  const long long b0 = s0 + (long long)blockIdx.x * NI_DRAIN_BLOCK;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  __syncthreads();
+  for (int k = threadIdx.x; k < NI_DRAIN_BLOCK; k += 256) {  // consecutive tiles of 256 slots, in slot order
+    const long long sl = b0 + k;
+    const unsigned tr = sl < s0 + count ? a.rec_traj[sl] : NI_REC_INVALID;
+    const bool valid = tr != NI_REC_INVALID;
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) warp_base[warp] = __popc(m);
+    __syncthreads();
+    unsigned before = running;
+    for (unsigned w = 0; w < warp; ++w) before += warp_base[w];
+    if (valid) {
+      const size_t o = before + __popc(m & ((1u << lane) - 1u));
+      o_traj[o] = tr;
+      o_t[o] = a.rec_t[sl];
+      for (int i = 0; i < n; ++i) o_y[o * n + i] = small ? a.rec_y[(long long)i * a.rec_cap + sl] : a.rec_y[sl * n + i];
+      for (int i = 0; i < Q; ++i) o_aux[o * Q + i] = small ? a.rec_aux[(long long)i * a.rec_cap + sl] : a.rec_aux[sl * Q + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned tot = 0;
+      for (int w = 0; w < 8; ++w) tot += warp_base[w];
+      running += tot;
+    }
+    __syncthreads();
   }
 }
 
@@ -1260,7 +1333,10 @@ NI_API int ni_ensemble_device_ptr(ni_ensemble *e, int field, void **dptr) {
   FieldInfo f;
   if (e && dptr && field >= NI_F_REC_TRAJ && field <= NI_F_REC_AUX) {
     if (e->a.rec_cap <= 0) return fail(NI_ERR_INVALID, "recording is not enabled");
-    void *ptrs[] = {e->a.rec_traj, e->a.rec_step, e->a.rec_t, e->a.rec_y, e->a.rec_aux};
+    if (field == NI_F_REC_STEP)
+      return fail(NI_ERR_UNSUPPORTED, "the log stores no step numbers: the records of a trajectory appear in step order "
+                  "(ni_ensemble_record_drain numbers them)");
+    void *ptrs[] = {e->a.rec_traj, nullptr, e->a.rec_t, e->a.rec_y, e->a.rec_aux};
     *dptr = ptrs[field - NI_F_REC_TRAJ];
     return NI_OK;
   }
@@ -1349,7 +1425,7 @@ NI_API int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity) {
     int rc = NI_OK;
     if (a.rec_cap > 0 || a.rec_traj) {  // growing: the old log goes (undrained records with it, as documented)
       CU(cudaStreamSynchronize(e->stream));
-      void *old[] = {a.rec_traj, a.rec_step, a.rec_t, a.rec_y, a.rec_aux};
+      void *old[] = {a.rec_traj, a.rec_t, a.rec_y, a.rec_aux};
       for (void *q : old) {
         if (!q) continue;
         for (size_t k = 0; k < e->allocs.size(); ++k)
@@ -1359,12 +1435,11 @@ NI_API int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity) {
           }
         cudaFree(q);
       }
-      a.rec_traj = a.rec_step = nullptr;
+      a.rec_traj = nullptr;
       a.rec_t = a.rec_y = a.rec_aux = nullptr;
       a.rec_cap = 0;
     }
     if (rc == NI_OK) rc = dalloc(e, &a.rec_traj, c);
-    if (rc == NI_OK) rc = dalloc(e, &a.rec_step, c);
     if (rc == NI_OK) rc = dalloc(e, &a.rec_t, c);
     if (rc == NI_OK) rc = dalloc(e, &a.rec_y, c * e->mod.n);
     if (rc == NI_OK) rc = dalloc(e, &a.rec_aux, c * e->mod.Q);
@@ -1391,57 +1466,65 @@ NI_API int ni_ensemble_record_count(ni_ensemble *e, int64_t *count) {
 NI_API int ni_ensemble_record_drain(ni_ensemble *e, uint32_t *traj, uint32_t *step, double *t, double *y, double *aux,
                                     int64_t max_records, int64_t *n_out) {
   if (!e || !n_out) return fail(NI_ERR_INVALID, "ensemble / n_out is NULL");
-  if (!traj) return fail(NI_ERR_INVALID, "the traj buffer is required (it marks unused slots)");
+  if (!traj) return fail(NI_ERR_INVALID, "the traj buffer is required");
   int64_t count = 0;
   if (int rc = ni_ensemble_record_count(e, &count)) return rc;
   if (count > max_records) return fail(NI_ERR_INVALID, "host buffers hold %lld records, the log has %lld", (long long)max_records, (long long)count);
   NiArgs &a = e->a;
-  const size_t c = (size_t)count;
-  const int n = e->mod.n, Q = e->mod.Q;
-  if (c > 0) {
-    if (traj) CU(cudaMemcpyAsync(traj, a.rec_traj, c * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (step) CU(cudaMemcpyAsync(step, a.rec_step, c * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (t) CU(cudaMemcpyAsync(t, a.rec_t, c * 8, cudaMemcpyDeviceToHost, e->stream));
-    if (y) {
-      if (e->mod.kind == NI_KIND_SMALL) {
-        if (int rc = need_scratch(e, c * n * 8)) return rc;
-        ni_k_rec_rows<<<grid_for((long long)c * n), 256, 0, e->stream>>>(a.rec_y, (double *)e->scratch, (long long)c, a.rec_cap, n);
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(y, e->scratch, c * n * 8, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-      } else {
-        CU(cudaMemcpyAsync(y, a.rec_y, c * n * 8, cudaMemcpyDeviceToHost, e->stream));
-      }
-    }
-    if (aux && Q > 0) {
-      if (e->mod.kind == NI_KIND_SMALL) {
-        if (int rc = need_scratch(e, c * Q * 8)) return rc;
-        ni_k_rec_rows<<<grid_for((long long)c * Q), 256, 0, e->stream>>>(a.rec_aux, (double *)e->scratch, (long long)c, a.rec_cap, Q);
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(aux, e->scratch, c * Q * 8, cudaMemcpyDeviceToHost, e->stream));
-      } else {
-        CU(cudaMemcpyAsync(aux, a.rec_aux, c * Q * 8, cudaMemcpyDeviceToHost, e->stream));
+  const int n = e->mod.n, Q = e->mod.Q, small = e->mod.kind == NI_KIND_SMALL ? 1 : 0;
+  // Windows of at most `window` slots are compacted on the device (unused slots dropped, order kept) into row-major
+  // staging buffers of fixed size -- the scratch does not grow with the log -- and copied out one after the other.
+  const long long rec_bytes = 4 + 8 + 8ll * n + 8ll * Q;
+  long long window = (256ll << 20) / rec_bytes / NI_DRAIN_BLOCK * NI_DRAIN_BLOCK;  // ~256 MB of staging
+  if (window < NI_DRAIN_BLOCK) window = NI_DRAIN_BLOCK;
+  if (window > count) window = (count + NI_DRAIN_BLOCK - 1) / NI_DRAIN_BLOCK * NI_DRAIN_BLOCK;
+  int64_t kept = 0;
+  if (count > 0) {
+    const long long max_blocks = window / NI_DRAIN_BLOCK;
+    const size_t off_t = ((size_t)window * 4 + 15) / 16 * 16, off_y = off_t + (size_t)window * 8,
+                 off_aux = off_y + (size_t)window * 8 * n, off_cnt = off_aux + (size_t)window * 8 * Q,
+                 off_tot = (off_cnt + (size_t)max_blocks * 4 + 15) / 16 * 16;
+    if (int rc = need_scratch(e, off_tot + 16)) return rc;
+    char *sc = (char *)e->scratch;
+    unsigned *o_traj = (unsigned *)sc, *blk = (unsigned *)(sc + off_cnt);
+    double *o_t = (double *)(sc + off_t), *o_y = (double *)(sc + off_y), *o_aux = (double *)(sc + off_aux);
+    unsigned long long *tot_d = (unsigned long long *)(sc + off_tot);
+    for (long long s0 = 0; s0 < count; s0 += window) {
+      const long long cnt = count - s0 < window ? count - s0 : window;
+      const int nb = (int)((cnt + NI_DRAIN_BLOCK - 1) / NI_DRAIN_BLOCK);
+      ni_k_drain_count<<<nb, 256, 0, e->stream>>>(a.rec_traj, s0, cnt, blk);
+      ni_k_drain_scan<<<1, 1024, 0, e->stream>>>(blk, nb, tot_d);
+      ni_k_drain_pack<<<nb, 256, 0, e->stream>>>(a, small, n, Q, s0, cnt, blk, o_traj, o_t, o_y, o_aux);
+      CU(cudaGetLastError());
+      unsigned long long k = 0;
+      CU(cudaMemcpyAsync(&k, tot_d, sizeof k, cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      if (k > 0) {
+        CU(cudaMemcpyAsync(traj + kept, o_traj, (size_t)k * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (t) CU(cudaMemcpyAsync(t + kept, o_t, (size_t)k * 8, cudaMemcpyDeviceToHost, e->stream));
+        if (y) CU(cudaMemcpyAsync(y + kept * n, o_y, (size_t)k * 8 * n, cudaMemcpyDeviceToHost, e->stream));
+        if (aux && Q > 0) CU(cudaMemcpyAsync(aux + kept * Q, o_aux, (size_t)k * 8 * Q, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));  // the staging buffers are reused by the next window
+        kept += (int64_t)k;
       }
     }
   }
   CU(cudaMemsetAsync(a.rec_cursor, 0, sizeof(unsigned long long), e->stream));
-  CU(cudaStreamSynchronize(e->stream));
-  // drop the slots that were reserved in chunks but never written (rec_traj == NI_REC_INVALID)
-  int64_t kept = count;
-  if (traj) {
-    kept = 0;
-    for (int64_t i = 0; i < count; ++i) {
-      if (traj[i] == NI_REC_INVALID) continue;
-      if (kept != i) {
-        traj[kept] = traj[i];
-        if (step) step[kept] = step[i];
-        if (t) t[kept] = t[i];
-        if (y) memcpy(y + kept * n, y + i * n, sizeof(double) * n);
-        if (aux && Q > 0) memcpy(aux + kept * Q, aux + i * Q, sizeof(double) * Q);
-      }
-      ++kept;
+  if (step && kept > 0) {
+    // The log stores no step numbers: the records of one trajectory appear in step order, and the last one of this
+    // batch is step n_accepted of the trajectory as it stands now (no kernel is running).
+    const size_t N = (size_t)e->N;
+    std::vector<int> nacc(N), seen(N, 0);
+    CU(cudaMemcpyAsync(nacc.data(), a.n_acc, N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int64_t i = 0; i < kept; ++i) ++seen[traj[i]];
+    for (size_t i = 0; i < N; ++i) {  // first step number of the batch, per trajectory
+      nacc[i] -= seen[i];
+      seen[i] = 0;
     }
+    for (int64_t i = 0; i < kept; ++i) step[i] = (uint32_t)(nacc[traj[i]] + ++seen[traj[i]]);
   }
+  CU(cudaStreamSynchronize(e->stream));
   *n_out = kept;
   return NI_OK;
 }

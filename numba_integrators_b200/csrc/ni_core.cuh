@@ -103,7 +103,8 @@ struct NiArgs {
   unsigned long long *rec_cursor;
   long long rec_cap;
   long long rec_chunk;          // slots a warp reserves per atomicAdd (0: exactly as many as it needs)
-  unsigned int *rec_traj, *rec_step;
+  unsigned int *rec_traj;       // trajectory of the record in a slot (NI_REC_INVALID: reserved, never written); the step
+                                // number is not stored: the records of one trajectory appear in step order
   double *rec_t, *rec_y, *rec_aux;  // rec_y [n][rec_cap], rec_aux [Q][rec_cap]
   // ff2cond: built-in predicate parameters
   int cond_kind;                // 0: no predicate; != 0: ff2cond launch of a kernel compiled with a predicate
@@ -614,7 +615,7 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
   for (int i = 0; i < (P > 0 ? P : 1); ++i) p[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < (Q > 0 ? Q : 1); ++i) aux[i] = 0.0;
-  int nacc = 0, status = NI_ST_RUNNING;  // nacc: REC only (step number of a record)
+  int status = NI_ST_RUNNING;
   int att_left = 0, acc_left = 0;
   // REC: this warp's reserved chunk of the record log: slots [rc_base + rc_off, rc_base + rc_len) are free.  The
   // chunk start is 64-bit and changes once per chunk; the per-attempt bookkeeping runs on the 32-bit offsets.
@@ -712,7 +713,6 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) aux[i] = a.aux[i * N + idx];
           }
-          if (REC) nacc = a.n_acc[idx];  // the record log tags every record with its step number
           att_left = max_att;
           acc_left = max_acc;
           last_accept = false;
@@ -865,7 +865,6 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) aux[i] = take ? auxn[i] : aux[i];
       }
-      if (REC) nacc += (int)accepted;
       acc_left -= (int)accepted;
       att_left -= (int)upd;
       last_accept = accepted;  // only read when the lane retires its trajectory, i.e. while `act`
@@ -873,7 +872,6 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
       if (REC && accepted) {
         const long long c = a.rec_cap;
         a.rec_traj[slot] = (unsigned int)idx;
-        a.rec_step[slot] = (unsigned int)nacc;
         a.rec_t[slot] = t;
 #pragma unroll
         for (int i = 0; i < n; ++i) a.rec_y[i * c + slot] = y[i];
@@ -959,8 +957,8 @@ static __device__ __noinline__ NiLeanCold ni_lean_cold(NiLeanColdIn<n> v, const 
 
 // ---------------------------------------------------------------- run kernel, lean variant
 // The same algorithm for the launches that need no per-attempt bookkeeping: reference semantics (SEM 0 / 1), no record
-// log, no predicate, max_step = inf, no attempt or accept budget (fast-forward; lock-step ni.step takes the general
-// body).  This is every benchmark launch but C2's.
+// log or a chunked one, no predicate, max_step = inf, no attempt or accept budget (fast-forward; lock-step ni.step
+// takes the general body).  This is every benchmark launch.
 //
 // Why a second body: the thread-per-trajectory kernel is bound by REGISTER-FILE READ BANDWIDTH, not by the FP64 pipe
 // (tools/micro/fp64_shadow.cu, profiles/r02_issue_model.txt: a scheduler reads two 32-bit register operands per lane
@@ -979,7 +977,7 @@ static __device__ __noinline__ NiLeanCold ni_lean_cold(NiLeanColdIn<n> v, const 
 //  * attempts are counted by a warp-uniform iteration counter (rejected = iterations in residency - accepted), status /
 //    step_size / running are derived at retirement, lanes without work are not masked: they run on benign values and
 //    cannot raise a flag.
-template <class Rhs, int METHOD, bool ADV, bool FAST>
+template <class Rhs, int METHOD, bool ADV, bool FAST, bool REC>
 NI_DEV void ni_small_run_lean(const NiArgs &a) {
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
   using Tab = NiTab<METHOD>;
@@ -997,14 +995,23 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
   for (int i = 0; i < (P > 0 ? P : 1); ++i) p[i] = 0.0;
   int status = NI_ST_RUNNING, nacc = 0, acc0 = 0, rej0 = 0;
   unsigned iter = 0, it0 = 0;  // hot-loop passes of this warp; the pass count at which the lane's trajectory was loaded
+  // REC: this warp's chunk of the record log: slots [rc_base + rc_off, rc_base + rc_len) are free.  An attempt only
+  // starts with room for all 32 lanes (the service branch renews the chunk), so an accepted step always has its slot and
+  // a full log stops trajectories BETWEEN attempts: nothing has to be undone.
+  long long rc_base = 0;
+  int rc_off = 0, rc_len = 0;
+  bool logfull = false;
+  const unsigned lanes_below = (1u << lane) - 1u;
   int kx = 0, tbk = 0x7fffffff;  // reach key: (hi(tn) ^ kx) >= tbk  <=  direction * (tn - t_bound) >= 0
   int xs = 0;                    // hi(h_abs) <u xs  <=  h_abs may be below 8 ulp(t) somewhere between t and t_bound
 
   const long long n_work = a.work_list ? (long long)*a.work_count : N;
-  // write the lane's trajectory back: it has finished / failed, or (`parking`) it moves to the next compaction pass
-  auto retire = [&](bool parking) {
+  // write the lane's trajectory back.  mode 0: it has finished / failed; 1: it moves to the next compaction pass;
+  // 2: the record log is full (it stays RUNNING until the host has drained the log)
+  auto retire = [&](int mode) {
+        const bool parking = mode == 1;
         const int n_attempts = (int)(iter - it0);
-        if (status == NI_ST_RUNNING && !parking) {
+        if (status == NI_ST_RUNNING && mode == 0) {
           status = NI_ST_FINISHED;
           // the terminal step() call of `while step(): pass` (_basic.py:135-136) overwrites step_size
           step_h = ADV ? h_abs : __dmul_rn(dir, h_abs);
@@ -1036,6 +1043,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         a.n_rej[idx] = rej0 + n_attempts - nacc;
         a.running[idx] = 0;
         if (parking) a.park_list[atomicAdd(a.queue + 4, 1ull)] = (unsigned int)idx;
+        if (mode == 2) atomicAdd(a.queue + 2, 1ull);
         if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
         active = false;
   };
@@ -1045,7 +1053,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     if (__any_sync(FULL, svc)) {
       // exit: the cold block latched a failure, or the last accepted step ended on t_bound (the reference's own test
       // at the top of its next step() call, _basic.py:135)
-      if (active && (status != NI_ST_RUNNING || __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0)) retire(false);
+      if (active && (status != NI_ST_RUNNING || __dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0)) retire(0);
       // refill: pop trajectories (warp-aggregated) until one is runnable or the queue is empty
       while (!active && !exhausted) {
         const unsigned grp = __activemask();
@@ -1054,7 +1062,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(grp));
         base = __shfl_sync(grp, base, leader);
         idx = (long long)(base + __popc(grp & ((1u << lane) - 1u)));
-        if (idx >= n_work) {
+        if (idx >= n_work || (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW))) {
           exhausted = true;
           break;
         }
@@ -1104,13 +1112,36 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         it0 = iter;
         active = true;
       }
+      if constexpr (REC) {
+        // (after the refill: a warp without work takes no chunk away from the others)
+        if (rc_len - rc_off < 32 && __any_sync(FULL, active)) {  // (warp-uniform) renew the chunk: leftover slots are marked unused
+          for (int o = rc_off + (int)lane; o < rc_len; o += 32) a.rec_traj[rc_base + o] = NI_REC_INVALID;
+          const long long want = a.rec_chunk;
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(a.rec_cursor, (unsigned long long)want);
+          rc_base = (long long)__shfl_sync(FULL, base, 0);
+          const long long avail = a.rec_cap - rc_base;
+          rc_off = 0;
+          rc_len = (int)(avail < 0 ? 0 : (avail < want ? avail : want));
+          if (rc_len < 32) {  // the log is full: no attempt starts, every trajectory of the warp waits for the drain
+            for (int o = (int)lane; o < rc_len; o += 32) a.rec_traj[rc_base + o] = NI_REC_INVALID;
+            rc_len = 0;
+            if (lane == 0) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+            logfull = true;
+          }
+        }
+        if (logfull || (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW)) {
+          if (logfull && active) retire(2);
+          exhausted = true;  // no new trajectory starts against a full log
+        }
+      }
       if (a.park_below > 0) {
         // compaction: the queue is empty and this warp is mostly idle -- its trajectories go to the next pass, where
         // they share full warps with the leftovers of the other warps (the state between two attempts is exactly
         // t, y, h_abs, K[-1])
         const int nact = __popc(__ballot_sync(FULL, active));
         if (nact > 0 && nact < a.park_below && __any_sync(FULL, exhausted)) {
-          if (active) retire(true);
+          if (active) retire(1);
           exhausted = true;
         }
       }
@@ -1170,7 +1201,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     // predicate registers (a flag merged across the cold call is materialised as a byte: six more instructions)
     // (bitwise, not short-circuit: nvcc otherwise threads the `active` test through the clamps above and duplicates them)
     const bool rare = active & ((out != 0u) | ((unsigned)__double2hiint(h_new) < (unsigned)xs));
-    bool cold = false;
+    bool cold = false, cold_acc = false;
     if (rare) {
       NiLeanColdIn<n> v;
 #pragma unroll
@@ -1191,6 +1222,10 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         status = c.status;
         step_h = h;  // step_size of the exit
       }
+      if (REC && (c.flags & 1)) {
+        cold_acc = true;
+        step_h = h;
+      }
       cold = true;  // the coming step entry is evaluated exactly in the service branch (8 ulp floor)
     }
     const bool take = ok && !rare;
@@ -1203,6 +1238,22 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     h_abs = h_new;
     if (take) ++nacc;
     ++iter;
+    if constexpr (REC) {
+      // one slot per accepting lane, handed out by ballot rank: consecutive lanes write consecutive slots
+      if (take) step_h = h;  // (a trajectory may leave RUNNING when the log fills up: its step_size must be current)
+      const bool recme = take | cold_acc;
+      const unsigned m = __ballot_sync(FULL, recme);
+      if (recme) {
+        const long long slot = rc_base + (rc_off + __popc(m & lanes_below)), c = a.rec_cap;
+        a.rec_traj[slot] = (unsigned int)idx;
+        a.rec_t[slot] = t;
+#pragma unroll
+        for (int i = 0; i < n; ++i) a.rec_y[i * c + slot] = y[i];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) a.rec_aux[i * c + slot] = auxn[i];
+      }
+      rc_off += __popc(m);
+    }
     // ---- step entry of the next attempt (_basic.py:145-156): h = +-h_abs, tn = t + h; the clip to t_bound is evaluated
     // exactly, but only by the lanes whose t + h may have reached t_bound (conservative key test: the last attempt of a
     // trajectory, 0.2 % of the lane-attempts); the 8 ulp floor of a step entry (:139-143) is the service branch's, which
@@ -1211,7 +1262,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
       const double hn = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
                             : h_abs;
       tn = __dadd_rn(t, hn);
-      svc = cold;
+      svc = REC ? (cold | (rc_len - rc_off < 32)) : cold;
       if ((__double2hiint(tn) ^ kx) >= tbk) {
         if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // (:135) t_bound has been reached: the trajectory leaves
           svc = true;
@@ -1228,15 +1279,19 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
       }
     }
   }
+  if constexpr (REC) {  // slots reserved but never written
+    for (int o = rc_off + (int)lane; o < rc_len; o += 32) a.rec_traj[rc_base + o] = NI_REC_INVALID;
+  }
 }
 
 template <class Rhs, int METHOD, int SEM, bool REC, bool FAST = false>
 NI_DEV void ni_small_run_body(const NiArgs &a) {
   const bool no_max_step = __double_as_longlong(a.max_step) == 0x7ff0000000000000LL && a.max_step_v == nullptr;
-  if constexpr (NI_LEAN && SEM != 2 && !REC && NI_COND == 0) {
-    // fast-forward without an attempt budget and with max_step = inf; lock-step ni.step takes the general body
-    if (no_max_step && a.max_attempts >= 0x7fffffffLL && a.max_accepts >= 0x7fffffffLL)
-      ni_small_run_lean<Rhs, METHOD, SEM == 1, FAST>(a);
+  if constexpr (NI_LEAN && SEM != 2 && NI_COND == 0) {
+    // fast-forward without an attempt budget and with max_step = inf (recording: chunked slot reservation, i.e. an
+    // ensemble of at least 65 536 trajectories); lock-step ni.step and everything else take the general body
+    if (no_max_step && a.max_attempts >= 0x7fffffffLL && a.max_accepts >= 0x7fffffffLL && (!REC || a.rec_chunk >= 32))
+      ni_small_run_lean<Rhs, METHOD, SEM == 1, FAST, REC>(a);
     else
       ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, true>(a);
   } else {

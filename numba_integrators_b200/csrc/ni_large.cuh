@@ -594,7 +594,6 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
             if (ni_large_j<Rhs>(c, i) < n) a.rec_y[slot * n + ni_large_j<Rhs>(c, i)] = y[i];
           if (tid == 0) {
             a.rec_traj[slot] = (unsigned int)idx;
-            a.rec_step[slot] = (unsigned int)nacc;
             a.rec_t[slot] = t;
           }
         }
