@@ -291,9 +291,11 @@ def main():
     value = acc_all * args.steps / (ms_max * 1e-3)
 
     # ---- the one collective of the path: final NCCL gather of terminal records (t, y, aux, counters, status)
-    def timed_gather(e, n_global, interleaved):
+    def timed_gather(e, n_global, interleaved, peer=False):
         from numba_integrators_b200 import distributed as nd
-        g = nd.TerminalGather(e, n_global, interleaved)
+        g = nd.PeerGather(e, n_global, interleaved) if peer else nd.TerminalGather(e, n_global, interleaved)
+        if peer and g.hdl is None:
+            return None, g.dtype.itemsize
         g.run()  # warm-up (NCCL channel setup, buffer registration)
         barrier()
         best = None
@@ -310,7 +312,9 @@ def main():
 
     gather_ms, strong = None, None
     if world > 1:
-        gather_ms, rec_bytes = timed_gather(ens, N * world, False)
+        gather_nccl_ms, rec_bytes = timed_gather(ens, N * world, False)
+        gather_peer_ms, _ = timed_gather(ens, N * world, False, peer=True)
+        gather_ms = min(x for x in (gather_nccl_ms, gather_peer_ms) if x is not None)
         # ---- strong scaling: the single-GPU problem (--traj trajectories IN TOTAL) sharded over the GPUs
         from numba_integrators_b200 import distributed as nd
         from numba_integrators_b200.workloads import Workload
@@ -327,10 +331,13 @@ def main():
         s_ms_max = reduce_max(s_ms)
         s_run_max = reduce_max(s_run)
         s_acc_all, s_att_all = reduce_sum(s_acc, s_att)
-        s_gather, _ = timed_gather(ens_s, args.traj, inter)
+        s_gather_nccl, _ = timed_gather(ens_s, args.traj, inter)
+        s_gather_peer, _ = timed_gather(ens_s, args.traj, inter, peer=True)
+        s_gather = min(x for x in (s_gather_nccl, s_gather_peer) if x is not None)
         step_ms = s_ms_max / args.steps
         strong = {'trajectories_total': args.traj, 'trajectories_per_gpu': len(idx), 'ms_per_step': step_ms,
                   'value': s_acc_all / (step_ms * 1e-3), 'final_gather_ms': s_gather,
+                  'final_gather_nccl_ms': s_gather_nccl, 'final_gather_peer_store_ms': s_gather_peer,
                   'ms_incl_gather': step_ms + s_gather, 'value_incl_gather': s_acc_all / ((step_ms + s_gather) * 1e-3),
                   'run_kernel_ms_max_over_ranks': s_run_max,
                   'gather_GBps_per_rank': rec_bytes * args.traj * (world - 1) / world / (s_gather * 1e-3) / 1e9,
@@ -477,6 +484,8 @@ def main():
             # figure; `value_incl_gather` charges it to every step)
             step_ms = ms_max / args.steps
             line['final_gather_ms'] = gather_ms
+            line['final_gather_nccl_ms'] = gather_nccl_ms  # pack kernel + ONE all_gather_into_tensor
+            line['final_gather_peer_store_ms'] = gather_peer_ms  # ONE kernel: pack + stores to every GPU over NVLink
             line['ms_incl_gather'] = step_ms + gather_ms
             line['value_incl_gather'] = acc_all / ((step_ms + gather_ms) * 1e-3)
             line['gather_GBps_per_rank'] = rec_bytes * N * (world - 1) / (gather_ms * 1e-3) / 1e9

@@ -212,6 +212,11 @@ int ni_ensemble_compaction(ni_ensemble *e, int park_below, int64_t *parked_last_
 int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory);
 int ni_ensemble_pack_terminal(ni_ensemble *e, void *dst_device);
 int ni_ensemble_get_terminal(ni_ensemble *e, void *host_out);
+/* Packing with the gather fused in: every packed word is stored to n_dst (<= 16) device buffers at once -- this GPU's
+ * slot in the receive buffer of every GPU of the job, peer memory reached over NVLink / NVSwitch (the caller maps the
+ * peers' buffers, e.g. torch.distributed._symmetric_memory, and synchronises the GPUs afterwards).  The transfer
+ * overlaps the packing; no staging copy and no library collective on the path. */
+int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_device, int n_dst);
 
 
 /* ---- recording of accepted steps into an HBM append log --------------------------------

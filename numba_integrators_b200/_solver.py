@@ -405,6 +405,12 @@ class Ensemble:
         check(self._L.ni_ensemble_get_terminal(self._h, _ptr(buf)))
         return out
 
+    def pack_terminal_peers(self, dst_device_ptrs):
+        """Pack the terminal records and store them to every buffer of `dst_device_ptrs` at once (peer memory of the
+        other GPUs: the fused gather of distributed.PeerGather)."""
+        arr = (_lib._vp * len(dst_device_ptrs))(*[int(p) for p in dst_device_ptrs])
+        check(self._L.ni_ensemble_pack_terminal_peers(self._h, arr, len(dst_device_ptrs)))
+
     def terminal(self):
         """The terminal records on the host: structured array (t, y, aux, n_accepted, n_rejected, status), one D2H copy."""
         out = np.empty(self.N, dtype=self.terminal_dtype())

@@ -23,6 +23,9 @@
 #include "ni_rhs_builtin.cuh"
 
 #define NI_API extern "C" __attribute__((visibility("default")))
+#ifndef NI_MAX_PEERS
+#define NI_MAX_PEERS 16  // destinations of ni_ensemble_pack_terminal_peers (GPUs of one NVSwitch domain)
+#endif
 
 extern const char ni_core_source[];   // ni_core.cuh as a string (generated: ni_core_src.cpp)
 extern const char ni_math_source[];   // ni_math.cuh as a string
@@ -1171,6 +1174,39 @@ __global__ void ni_k_pack_terminal(NiArgs a, int small, int n, int Q, unsigned *
   }
 }
 
+// The same packing with the gather fused in: every word is stored to `nd` destinations -- this GPU's slot in the
+// receive buffer of every rank, peer memory reached over NVLink / NVSwitch (symmetric-memory allocations whose peer
+// addresses the caller obtained at rendezvous).  The transfer overlaps the packing word by word; no staging copy, no
+// library collective.  Completion on the peers is the caller's barrier.
+struct NiPeerDst {
+  unsigned *p[NI_MAX_PEERS];
+  int nd;
+};
+__global__ void ni_k_pack_terminal_peers(NiArgs a, int small, int n, int Q, NiPeerDst d) {
+  const int dwords = 2 * (1 + n + Q), W = dwords + 3;
+  const long long total = a.N * W;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long i = g / W;
+    const int w = (int)(g - i * W);
+    unsigned out;
+    if (w < dwords) {
+      const int c = w >> 1;
+      double v;
+      if (c == 0)
+        v = a.t[i];
+      else if (c <= n)
+        v = small ? (a.y_rows ? a.y_rows[i * n + (c - 1)] : a.y[(long long)(c - 1) * a.N + i]) : a.y[i * n + (c - 1)];
+      else
+        v = small ? a.aux[(long long)(c - 1 - n) * a.N + i] : a.aux[i * Q + (c - 1 - n)];
+      out = (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
+    } else {
+      const int k = w - dwords;
+      out = (unsigned)(k == 0 ? a.n_acc[i] : k == 1 ? a.n_rej[i] : a.status[i]);
+    }
+    for (int r = 0; r < d.nd; ++r) d.p[r][g] = out;
+  }
+}
+
 static int grid_for(long long work) {
   long long g = (work + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -1397,6 +1433,24 @@ NI_API int ni_ensemble_pack_terminal(ni_ensemble *e, void *dst_device) {
   const long long words = (long long)e->N * (2 * (1 + e->mod.n + e->mod.Q) + 3);
   ni_k_pack_terminal<<<grid_for(words), 256, 0, e->stream>>>(e->a, e->mod.kind == NI_KIND_SMALL ? 1 : 0, e->mod.n, e->mod.Q,
                                                              (unsigned *)dst_device);
+  CU(cudaGetLastError());
+  e->n_launches++;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_device, int n_dst) {
+  if (!e || !dst_device || n_dst < 1 || n_dst > NI_MAX_PEERS)
+    return fail(NI_ERR_INVALID, "need an ensemble and 1..%d destination buffers", NI_MAX_PEERS);
+  if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
+  CU(cudaSetDevice(e->device));
+  NiPeerDst d;
+  d.nd = n_dst;
+  for (int r = 0; r < NI_MAX_PEERS; ++r) d.p[r] = r < n_dst ? (unsigned *)dst_device[r] : nullptr;
+  for (int r = 0; r < n_dst; ++r)
+    if (!d.p[r]) return fail(NI_ERR_INVALID, "destination %d is NULL", r);
+  const long long words = (long long)e->N * (2 * (1 + e->mod.n + e->mod.Q) + 3);
+  ni_k_pack_terminal_peers<<<grid_for(words), 256, 0, e->stream>>>(e->a, e->mod.kind == NI_KIND_SMALL ? 1 : 0, e->mod.n,
+                                                                   e->mod.Q, d);
   CU(cudaGetLastError());
   e->n_launches++;
   return NI_OK;

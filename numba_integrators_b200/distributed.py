@@ -115,6 +115,53 @@ class TerminalGather:
         return merge_records(recs, self.N, self.world, self.interleaved)
 
 
+class PeerGather(TerminalGather):
+    """The same gather without a library collective: ONE kernel packs the terminal records and stores every word
+    straight into this rank's slot of EVERY rank's receive buffer -- peer memory over NVLink / NVSwitch
+    (torch.distributed._symmetric_memory maps the buffers of the other processes at rendezvous) -- so the transfer
+    overlaps the packing and nothing is staged; a symmetric-memory barrier on either side orders it against the peers'
+    reads.  Falls back to the NCCL collective of `TerminalGather` where symmetric memory is not available."""
+
+    def __init__(self, ens, N_global, interleaved=False, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ens, self.N, self.interleaved, self.to_rank0 = ens, int(N_global), interleaved, False
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.dtype = ens.terminal_dtype()
+        self.rows = shard_rows(self.N, self.world)
+        own = len(shard_indices(self.N, self.rank, self.world, interleaved))
+        if own != ens.N:
+            raise ValueError(f'rank {self.rank} holds {ens.N} trajectories, the sharding rule gives it {own} of {self.N}')
+        nbytes = self.rows * self.dtype.itemsize
+        dev = torch.device('cuda', ens.device)
+        self.hdl = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.recv = symm_mem.empty((self.world, nbytes), dtype=torch.uint8, device=dev)
+            self.recv.zero_()
+            self.hdl = symm_mem.rendezvous(self.recv, self.group)
+            # where this rank's rows live in every rank's receive buffer
+            self.dst = [int(self.hdl.buffer_ptrs[r]) + self.rank * nbytes for r in range(self.world)]
+        except Exception as exc:  # no symmetric memory on this system / backend: the NCCL collective
+            self.fallback_reason = f'{type(exc).__name__}: {exc}'
+            self.recv = torch.zeros((self.world, nbytes), dtype=torch.uint8, device=dev)
+        self.send = self.recv[self.rank]
+
+    @property
+    def impl(self):
+        return 'peer stores over NVLink (symmetric memory), fused with the packing kernel' if self.hdl is not None \
+            else 'NCCL all_gather_into_tensor'
+
+    def run(self):
+        if self.hdl is None:
+            return TerminalGather.run(self)
+        self.hdl.barrier()                       # every rank is done reading the previous contents
+        self.ens.pack_terminal_peers(self.dst)   # (the ensemble runs on torch's current stream, like the barriers)
+        self.hdl.barrier()                       # every rank's stores have landed
+        return self.recv
+
+
 def merge_records(recs, N, world, interleaved=False):
     """(world, rows) structured terminal records -> dict of (N, ...) arrays in global trajectory order."""
     out = None
@@ -157,11 +204,12 @@ def merge_shards(parts, N, world, interleaved=False):
     return out
 
 
-def gather(ens, N_global=None, interleaved=False, group=None):
+def gather(ens, N_global=None, interleaved=False, group=None, peer=False):
     """Final gather of terminal t, y, auxiliary and the step statistics of a sharded ensemble.
 
     Every rank receives the full arrays in global trajectory order (numpy, host): one pack kernel, one NCCL
-    all-gather of equal-sized record slots, one D2H copy."""
+    all-gather of equal-sized record slots (or, `peer=True`, one kernel that packs and stores to every GPU's buffer
+    over NVLink: PeerGather), one D2H copy."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -169,8 +217,11 @@ def gather(ens, N_global=None, interleaved=False, group=None):
         n = torch.tensor([ens.N], dtype=torch.int64, device=torch.device('cuda', ens.device))
         dist.all_reduce(n, group=group)
         N_global = int(n.item())
-    g = TerminalGather(ens, N_global, interleaved, group)
+    g = PeerGather(ens, N_global, interleaved, group) if peer else TerminalGather(ens, N_global, interleaved, group)
     ens.sync()
+    if peer:
+        import torch.cuda
+        ens.set_stream(torch.cuda.current_stream().cuda_stream)  # the symmetric-memory barriers run on torch's stream
     g.run()
     torch.cuda.synchronize()
     return g.host()

@@ -31,6 +31,8 @@ for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False)
         ens = ni.RK23(f(*arrays['params'].T), w.t0, arrays['y0'], w.t_bound, rtol=w.rtol, atol=w.atol)
     ens.run()
     full = nd.gather(ens, N_global=w.N, interleaved=interleaved)
+    full_p = nd.gather(ens, N_global=w.N, interleaved=interleaved, peer=True)  # fused pack + peer stores over NVLink
+    same_p = all(np.array_equal(full[k], full_p[k]) for k in full)
     if rank == 0:
         if w.advanced:
             ref = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, w.y0, w.params, w.t_bound, rtol=w.rtol, atol=w.atol)
@@ -42,8 +44,9 @@ for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False)
                 and np.array_equal(full['status'], ref.status))
         if w.advanced:
             same = same and np.array_equal(full['auxiliary'], ref.auxiliary)
+        same = same and same_p
         print(f'{name}: world={world} N={w.N} shard sizes ~{len(idx)} interleaved={interleaved} '
-              f'gather == single-GPU run: {same}; accepted {int(full["n_accepted"].sum())}')
+              f'gather (NCCL and peer-store) == single-GPU run: {same}; accepted {int(full["n_accepted"].sum())}')
         ok = ok and same
 flag = torch.tensor([1 if ok else 0], device='cuda')
 dist.broadcast(flag, 0)
