@@ -229,15 +229,41 @@ class Ensemble:
             return a[0].item() if a.ndim == 1 else a[0]
         return a
 
-    t = property(lambda s: s._scalar_or_array(s._get(_lib.F_T, None)))
-    y = property(lambda s: s._scalar_or_array(s._get(_lib.F_Y, s.n)))
+    # The reference's jitclass fields are plain attributes (_basic.py:182-199): everything that is state can also be
+    # assigned (the caller keeps t, y and K[-1] consistent, exactly as with the reference).
+    def _set_rows(self, field, value, comps):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (self.N, comps)))
+        check(self._L.ni_ensemble_set(self._h, field, a.ctypes.data))
+
+    @property
+    def t(self):
+        return self._scalar_or_array(self._get(_lib.F_T, None))
+
+    @t.setter
+    def t(self, value):
+        self._set(_lib.F_T, value)
+
+    @property
+    def y(self):
+        return self._scalar_or_array(self._get(_lib.F_Y, self.n))
+
+    @y.setter
+    def y(self, value):
+        self._set_rows(_lib.F_Y, value, self.n)
+
     @property
     def auxiliary(self):
         a = self._get(_lib.F_AUX, self.Q)
         if getattr(self.fun, 'aux_scalar', False):  # the Python RHS returned a scalar auxiliary (README.md:84)
             a = a[:, 0]
         return self._scalar_or_array(a)
-    step_size = property(lambda s: s._scalar_or_array(s._get(_lib.F_STEP_SIZE, None)))
+    @property
+    def step_size(self):
+        return self._scalar_or_array(self._get(_lib.F_STEP_SIZE, None))
+
+    @step_size.setter
+    def step_size(self, value):
+        self._set(_lib.F_STEP_SIZE, value)
 
     @property
     def max_step(self):  # _basic.py:188: a scalar field of the jitclass; one value per trajectory when given as an array
@@ -284,11 +310,18 @@ class Ensemble:
     def K(self):
         """Stage matrix (n_stages+1, n).  Only K[-1] (the FSAL stage, the one that carries state
         between steps) is kept on the device; rows 0..n_stages-1 are scratch in the reference
-        (overwritten by every attempt) and read NaN here."""
+        (overwritten by every attempt) and read NaN here.  Assigning K writes K[-1]."""
         kl = self._get(_lib.F_KLAST, self.n)
         K = np.full((self.N, self.n_stages + 1, self.n), np.nan)
         K[:, -1, :] = kl
         return K[0] if self._single else K
+
+    @K.setter
+    def K(self, value):
+        v = np.asarray(value, dtype=np.float64)
+        if v.shape[-2:] == (self.n_stages + 1, self.n):  # a whole stage matrix: only the FSAL row is state
+            v = v[..., -1, :]
+        self._set_rows(_lib.F_KLAST, v, self.n)
 
     @property
     def state(self):  # _basic.py:269-271 / _advanced.py:276-278

@@ -1048,15 +1048,23 @@ __global__ void ni_k_tbound(NiArgs a, int mode, double t_end, double *saved, uns
       const bool not_last = tb > t_end;
       flag[i] = not_last ? 1 : 0;
       if (not_last) tb = t_end;
-    } else {  // ff2t end (_API.py:37)
+    } else if (mode == 2) {  // ff2t end (_API.py:37)
       tb = saved[i];
-    }
+    }  // mode 3: t / direction were overwritten, only the finished <-> running status below is re-evaluated
     a.t_bound[i] = tb;
     if (a.status[i] == NI_ST_FINISHED && !(a.direction[i] * (a.t[i] - tb) >= 0.0)) a.status[i] = NI_ST_RUNNING;
   }
 }
 
 // component-major [c][N] <-> row-major [N][c]
+// row-major [N][c] -> component-major [c][N] (field writes of the thread-per-trajectory layout)
+__global__ void ni_k_from_rows(const double *src, double *dst, long long N, int c) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < N * c; k += (long long)gridDim.x * blockDim.x) {
+    const long long i = k / c;
+    const int j = (int)(k - i * c);
+    dst[(long long)j * N + i] = src[k];
+  }
+}
 __global__ void ni_k_to_rows(const double *src, double *dst, long long N, int c) {
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < N * c; k += (long long)gridDim.x * blockDim.x) {
     const long long i = k / c;
@@ -1182,28 +1190,49 @@ struct NiPeerDst {
   unsigned *p[NI_MAX_PEERS];
   int nd;
 };
+// one 32-bit word of the packed terminal records: word w of trajectory i
+__device__ __forceinline__ unsigned ni_terminal_word(const NiArgs &a, int small, int n, int Q, int dwords, long long i, int w) {
+  if (w < dwords) {
+    const int c = w >> 1;
+    double v;
+    if (c == 0)
+      v = a.t[i];
+    else if (c <= n)
+      v = small ? (a.y_rows ? a.y_rows[i * n + (c - 1)] : a.y[(long long)(c - 1) * a.N + i]) : a.y[i * n + (c - 1)];
+    else
+      v = small ? a.aux[(long long)(c - 1 - n) * a.N + i] : a.aux[i * Q + (c - 1 - n)];
+    return (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
+  }
+  const int k = w - dwords;
+  return (unsigned)(k == 0 ? a.n_acc[i] : k == 1 ? a.n_rej[i] : a.status[i]);
+}
+// Tiles of NI_PACK_TILE trajectories (a multiple of 4, so a tile starts on a 16-byte boundary of the packed buffer);
+// inside a tile the (trajectory, word) split is a 32-bit division.  16-byte stores: a warp sends 512 contiguous bytes
+// per destination and instruction over NVLink.
+#define NI_PACK_TILE 1024
 __global__ void ni_k_pack_terminal_peers(NiArgs a, int small, int n, int Q, NiPeerDst d) {
   const int dwords = 2 * (1 + n + Q), W = dwords + 3;
-  const long long total = a.N * W;
-  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-    const long long i = g / W;
-    const int w = (int)(g - i * W);
-    unsigned out;
-    if (w < dwords) {
-      const int c = w >> 1;
-      double v;
-      if (c == 0)
-        v = a.t[i];
-      else if (c <= n)
-        v = small ? (a.y_rows ? a.y_rows[i * n + (c - 1)] : a.y[(long long)(c - 1) * a.N + i]) : a.y[i * n + (c - 1)];
-      else
-        v = small ? a.aux[(long long)(c - 1 - n) * a.N + i] : a.aux[i * Q + (c - 1 - n)];
-      out = (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
-    } else {
-      const int k = w - dwords;
-      out = (unsigned)(k == 0 ? a.n_acc[i] : k == 1 ? a.n_rej[i] : a.status[i]);
+  const long long tiles = (a.N + NI_PACK_TILE - 1) / NI_PACK_TILE;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long i0 = tile * NI_PACK_TILE;
+    const unsigned rows = (unsigned)(a.N - i0 < NI_PACK_TILE ? a.N - i0 : NI_PACK_TILE);
+    const unsigned words = rows * (unsigned)W, quads = words >> 2;
+    const long long g0 = i0 * W;  // a multiple of 4
+    for (unsigned q = threadIdx.x; q < quads; q += blockDim.x) {
+      unsigned o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned gl = 4u * q + k, il = gl / (unsigned)W;
+        o[k] = ni_terminal_word(a, small, n, Q, dwords, i0 + il, (int)(gl - il * (unsigned)W));
+      }
+      const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+      for (int r = 0; r < d.nd; ++r) ((uint4 *)(d.p[r] + g0))[q] = v;
     }
-    for (int r = 0; r < d.nd; ++r) d.p[r][g] = out;
+    if (threadIdx.x < (words & 3u)) {  // the last 1..3 words of the buffer (only the last tile can have them)
+      const unsigned gl = (quads << 2) + threadIdx.x, il = gl / (unsigned)W;
+      const unsigned out = ni_terminal_word(a, small, n, Q, dwords, i0 + il, (int)(gl - il * (unsigned)W));
+      for (int r = 0; r < d.nd; ++r) d.p[r][g0 + gl] = out;
+    }
   }
 }
 
@@ -1410,10 +1439,31 @@ NI_API int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in) {
     CU(cudaMemcpyAsync(e->scratch, host_in, N * 8, cudaMemcpyHostToDevice, e->stream));
     ni_k_tbound<<<grid_for(e->N), 256, 0, e->stream>>>(e->a, 0, 0.0, e->tb_saved, e->flag_d, (const double *)e->scratch);
     CU(cudaGetLastError());
-  } else if (field == NI_F_H_ABS) {
-    CU(cudaMemcpyAsync(e->a.h_abs, host_in, N * 8, cudaMemcpyHostToDevice, e->stream));
-  } else {
+  } else if (field == NI_F_STATUS || field == NI_F_N_ACCEPTED || field == NI_F_N_REJECTED || field == NI_F_RUNNING ||
+             field == NI_F_COND_HIT || field == NI_F_PARAMS) {
     return fail(NI_ERR_INVALID, "field %d is read-only", field);
+  } else {
+    // the state fields of the reference's jitclass are plain attributes (_basic.py:182-199): t, y, h_abs, step_size,
+    // direction, K[-1] and the auxiliary output can be overwritten between calls; the caller keeps them consistent
+    FieldInfo f;
+    if (!field_info(e, field, &f) || !f.is_double) return fail(NI_ERR_INVALID, "field %d cannot be written", field);
+    if (f.comps == 0) return NI_OK;
+    if (f.comps > 1 && e->mod.kind == NI_KIND_SMALL) {  // rows on the host, component-major on the device
+      if (int rc = need_scratch(e, N * f.comps * 8)) return rc;
+      CU(cudaMemcpyAsync(e->scratch, host_in, N * f.comps * 8, cudaMemcpyHostToDevice, e->stream));
+      ni_k_from_rows<<<grid_for((long long)N * f.comps), 256, 0, e->stream>>>((const double *)e->scratch, (double *)f.ptr, (long long)N, f.comps);
+      CU(cudaGetLastError());
+      if (field == NI_F_Y && e->a.y_rows)
+        CU(cudaMemcpyAsync(e->a.y_rows, e->scratch, N * f.comps * 8, cudaMemcpyDeviceToDevice, e->stream));
+    } else {
+      CU(cudaMemcpyAsync(f.ptr, host_in, N * f.comps * 8, cudaMemcpyHostToDevice, e->stream));
+      if (field == NI_F_Y && e->a.y_rows)
+        CU(cudaMemcpyAsync(e->a.y_rows, host_in, N * f.comps * 8, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (field == NI_F_T || field == NI_F_DIRECTION) {  // a finished trajectory may be running again (and vice versa)
+      ni_k_tbound<<<grid_for(e->N), 256, 0, e->stream>>>(e->a, 3, 0.0, e->tb_saved, e->flag_d, nullptr);
+      CU(cudaGetLastError());
+    }
   }
   CU(cudaStreamSynchronize(e->stream));
   return NI_OK;
@@ -1426,10 +1476,15 @@ NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_t
   return NI_OK;
 }
 
+NI_API int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_device, int n_dst);
 NI_API int ni_ensemble_pack_terminal(ni_ensemble *e, void *dst_device) {
   if (!e || !dst_device) return fail(NI_ERR_INVALID, "ensemble / dst_device is NULL");
   if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
   CU(cudaSetDevice(e->device));
+  if (((uintptr_t)dst_device & 15) == 0) {  // the tiled kernel with 16-byte stores (one destination)
+    void *one[1] = {dst_device};
+    return ni_ensemble_pack_terminal_peers(e, one, 1);
+  }
   const long long words = (long long)e->N * (2 * (1 + e->mod.n + e->mod.Q) + 3);
   ni_k_pack_terminal<<<grid_for(words), 256, 0, e->stream>>>(e->a, e->mod.kind == NI_KIND_SMALL ? 1 : 0, e->mod.n, e->mod.Q,
                                                              (unsigned *)dst_device);
@@ -1448,8 +1503,12 @@ NI_API int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_devi
   for (int r = 0; r < NI_MAX_PEERS; ++r) d.p[r] = r < n_dst ? (unsigned *)dst_device[r] : nullptr;
   for (int r = 0; r < n_dst; ++r)
     if (!d.p[r]) return fail(NI_ERR_INVALID, "destination %d is NULL", r);
+  for (int r = 0; r < n_dst; ++r)
+    if ((uintptr_t)d.p[r] & 15) return fail(NI_ERR_INVALID, "destination %d is not 16-byte aligned", r);
   const long long words = (long long)e->N * (2 * (1 + e->mod.n + e->mod.Q) + 3);
-  ni_k_pack_terminal_peers<<<grid_for(words), 256, 0, e->stream>>>(e->a, e->mod.kind == NI_KIND_SMALL ? 1 : 0, e->mod.n,
+  (void)words;
+  const long long tiles = (e->N + NI_PACK_TILE - 1) / NI_PACK_TILE;
+  ni_k_pack_terminal_peers<<<(int)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, e->stream>>>(e->a, e->mod.kind == NI_KIND_SMALL ? 1 : 0, e->mod.n,
                                                                    e->mod.Q, d);
   CU(cudaGetLastError());
   e->n_launches++;

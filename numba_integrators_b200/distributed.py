@@ -67,6 +67,11 @@ def device_tensors(ens):
     return out, small
 
 
+def _slot_bytes(rows, dtype):
+    """Bytes of one rank's slot in the gather buffer: the records, padded to 16 bytes (vector stores over NVLink)."""
+    return (rows * dtype.itemsize + 15) // 16 * 16
+
+
 def shard_rows(N, world):
     """Rows of the gather buffer per rank: the largest shard (equal-sized slots, no size exchange: every rank
     derives every shard's length from N and the sharding rule)."""
@@ -93,7 +98,7 @@ class TerminalGather:
         if own != ens.N:
             raise ValueError(f'rank {self.rank} holds {ens.N} trajectories, the sharding rule gives it {own} of {self.N}')
         dev = torch.device('cuda', ens.device)
-        nbytes = self.rows * self.dtype.itemsize
+        nbytes = self.slot_bytes = _slot_bytes(self.rows, self.dtype)
         # own slot is part of the receive buffer: the pack kernel writes where the collective reads (in place)
         self.recv = torch.zeros((self.world, nbytes), dtype=torch.uint8, device=dev)
         self.send = self.recv[self.rank]
@@ -111,7 +116,8 @@ class TerminalGather:
 
     def host(self):
         """The gathered records as numpy arrays in GLOBAL trajectory order (one D2H copy)."""
-        recs = self.recv.cpu().numpy().view(self.dtype).reshape(self.world, self.rows)
+        used = self.rows * self.dtype.itemsize
+        recs = np.ascontiguousarray(self.recv.cpu().numpy()[:, :used]).view(self.dtype).reshape(self.world, self.rows)
         return merge_records(recs, self.N, self.world, self.interleaved)
 
 
@@ -133,7 +139,7 @@ class PeerGather(TerminalGather):
         own = len(shard_indices(self.N, self.rank, self.world, interleaved))
         if own != ens.N:
             raise ValueError(f'rank {self.rank} holds {ens.N} trajectories, the sharding rule gives it {own} of {self.N}')
-        nbytes = self.rows * self.dtype.itemsize
+        nbytes = self.slot_bytes = _slot_bytes(self.rows, self.dtype)
         dev = torch.device('cuda', ens.device)
         self.hdl = None
         try:

@@ -550,3 +550,41 @@ def test_long_lock_step_loop_uses_the_graph_path_and_matches_fast_forward():
     assert np.array_equal(s2.n_accepted, ref.n_accepted)
     # the ff2t leg changes the step sequence, so only the end point is comparable
     assert np.all(s.t == 30.0) and np.allclose(s.y, ref.y, rtol=1e-7, atol=1e-9)
+
+
+def test_state_fields_are_assignable_like_jitclass_attributes():
+    """_basic.py:182-199: the solver's fields are plain jitclass attributes.  Restarting a trajectory from a stored
+    (t, y, h_abs, K[-1]) -- the complete state between two steps -- continues it bit for bit, on both layouts."""
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c3_lorenz(N=500, t_bound=2.0)
+    Solver = ni.Advanced(3, 1, ni.RK45)
+    a = Solver(ni.rhs.lorenz63, 0.0, w.y0, w.params, 2.0, rtol=1e-8, atol=1e-8)
+    for _ in range(40):
+        ni.step(a)
+    snap = (a.t, a.y, a.h_abs, a.K, a.step_size)
+    assert a.run() == 0
+    b = Solver(ni.rhs.lorenz63, 0.0, w.y0 * 0.5 + 1.0, w.params, 2.0, rtol=1e-8, atol=1e-8)   # a different history
+    b.t, b.y, b.h_abs, b.K, b.step_size = snap
+    assert np.array_equal(b.t, snap[0]) and np.array_equal(b.y, snap[1]) and np.array_equal(b.K[:, -1], snap[3][:, -1])
+    assert b.run() == 0
+    assert np.array_equal(b.y, a.y) and np.array_equal(b.t, a.t) and np.array_equal(b.h_abs, a.h_abs)
+    assert np.array_equal(b.auxiliary, a.auxiliary)
+    # single solver, scalar attribute; assigning t past t_bound finishes it
+    s = ni.RK45(ni.rhs.harmonic, 0.0, np.array((0., 1.)), t_bound=1, atol=1e-8, rtol=1e-8)
+    s.y = np.array((0.5, 0.5))
+    assert np.array_equal(s.y, [0.5, 0.5])
+    s.t = 1.0
+    assert not ni.step(s) and s.t == 1.0
+    with pytest.raises(ni.NiError):
+        s._set(7, 1.0)                      # n_accepted and the other bookkeeping fields stay read-only
+    # CTA-per-trajectory layout
+    h = wl.c5_heat(N=3, n=200, t_bound=1.0)
+    c = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 1.0, rtol=1e-8, atol=1e-8)
+    for _ in range(5):
+        ni.step(c)
+    snap = (c.t, c.y, c.h_abs, c.K)
+    c.run()
+    d = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0 * 0.3, 1.0, rtol=1e-8, atol=1e-8)
+    d.t, d.y, d.h_abs, d.K = snap
+    d.run()
+    assert np.array_equal(d.y, c.y) and np.array_equal(d.n_accepted + 0, d.n_accepted)
