@@ -242,7 +242,11 @@ int ni_fp64_peak(int device, int iters, int repeats, double *tflops_best);
 /* device self-check of the branch-free arithmetic of the error-norm / controller tail (csrc/ni_math.cuh):
  * `count` random operands inside the guarded ranges; which = 0: ni_div_core against `/`, 1: ni_sqrt_core against
  * sqrt(), 2 / 3: ni_pow_ctrl_ms<5> / <3> (seeded from the mean square) against ni_pow_ctrl on the root.
- * *mismatches = results that differ in any bit (0 expected for 0 and 1; a few per 10^5 at most for 2 and 3). */
+ * *mismatches = results that differ in any bit (0 expected for 0 and 1; a few per 10^5 at most for 2 and 3).
+ * which = 5: ni_div_core over the operand range the lean run body's guard admits (scales in [2^-200, 2^1020), any
+ * error): violations of "bit-identical where the IEEE quotient is normal, non-finite where it overflows, negligible
+ * otherwise".  which = 4: *mismatches = the largest |1 - b r| of the reciprocal r that ni_div_core multiplies with, in
+ * units of 2^-64 (the quotient is correctly rounded unless it lies within ~|1 - b r| * 2^-52 of a rounding boundary). */
 int ni_devmath_check(int device, int which, int64_t count, uint64_t seed, int64_t *mismatches);
 
 #ifdef __cplusplus

@@ -810,10 +810,13 @@ NI_API int ni_ensemble_reset(ni_ensemble *e, const double *rtol, const double *a
   CU(cudaSetDevice(e->device));
   const int n = e->mod.n;
   if (e->mod.kind == NI_KIND_SMALL) {
+    bool floor_ok = true;
     for (int i = 0; i < n; ++i) {
       e->a.rtol[i] = rtol[i];
       e->a.atol[i] = atol[i];
+      floor_ok = floor_ok && atol[i] >= 6.223015277861142e-61 && atol[i] < INFINITY;  // 2^-200 (ni_guard_lite_out)
     }
+    e->a.atol_floor = floor_ok ? 1 : 0;
   } else {
     bool uni = true;
     for (int i = 1; i < n; ++i) uni = uni && rtol[i] == rtol[0] && atol[i] == atol[0];

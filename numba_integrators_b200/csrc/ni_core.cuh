@@ -86,6 +86,8 @@ struct NiArgs {
   int n;                        // large kernels: state dimension (run-time)
   const double *rtol_d, *atol_d;  // large kernels: tolerance vectors in HBM (n entries)
   int tol_uniform;              // large kernels: every component has rtol[0] / atol[0]
+  int atol_floor;               // small kernels: every atol[i] is finite and >= 2^-200, so every error scale is (the
+                                // lean run body's division guard then only watches the upper end)
   int compat;                   // 0: the reference's step semantics; 1: scipy.integrate semantics
   unsigned char *step_rejected; // compat == 1: "a rejection happened in the current step" (scipy's step_rejected)
   unsigned long long *queue;    // [0] work cursor, [1] flags, [2] #retired still RUNNING, [3] #last step accepted,
@@ -393,7 +395,7 @@ NI_DEV double ni_absmax(double a, double b) {
 // zero, denormal or non-finite error: the caller redoes the tail with the operators from `num`).  Fast arithmetic:
 // `en` is the MEAN SQUARE error and the caller takes the controller power (ni_pow_fast*).
 // kl = K[0] = K[-1] of the previous attempt: stale after a rejection (_basic.py:151).
-template <class Rhs, int METHOD, bool FAST>
+template <class Rhs, int METHOD, bool FAST, bool LITE = false>
 NI_DEV void ni_rk_attempt(const NiArgs &a, double t, double tn, double h, const double (&y)[Rhs::N],
                           const double (&kl)[Rhs::N], const double (&p)[Rhs::P > 0 ? Rhs::P : 1], double (&yn)[Rhs::N],
                           double (&kn)[Rhs::N], double (&auxn)[Rhs::Q > 0 ? Rhs::Q : 1], double (&num)[Rhs::N],
@@ -436,11 +438,17 @@ NI_DEV void ni_rk_attempt(const NiArgs &a, double t, double tn, double h, const 
   } else {
     double q[n];
     NiDivGuard guard = ni_guard_begin();
+    int den_hi = 0;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       num[i] = __dmul_rn(ev[i], h);
       const double den = __dadd_rn(a.atol[i], __dmul_rn(ni_absmax(y[i], yn[i]), a.rtol[i]));
-      ni_guard_add(guard, num[i], den);
+      if constexpr (LITE) {
+        const int hb = __double2hiint(den);
+        den_hi = hb > den_hi ? hb : den_hi;
+      } else {
+        ni_guard_add(guard, num[i], den);
+      }
       q[i] = ni_div_core(num[i], den);
       kn[i] = K[S][i];
     }
@@ -449,7 +457,9 @@ NI_DEV void ni_rk_attempt(const NiArgs &a, double t, double tn, double h, const 
     for (int i = 1; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(q[i], q[i]));
     // acc / n (_aux.py:75): exact for n = 1, 2; Markstein for n = 3; the guard on ms below covers acc otherwise
     const double ms = n == 1 ? acc : n == 2 ? __dmul_rn(acc, 0.5) : n == 3 ? ni_div3(acc) : ni_div_core(acc, (double)n);
-    out = ni_guard_out(guard) | ni_sqrt_out(ms);
+    // LITE (the caller knows that every scale is >= 2^-200: NiArgs::atol_floor): only the upper end of the scales is
+    // watched -- see ni_guard_lite_out in ni_math.cuh for why the errors need no test of their own
+    out = (LITE ? ni_guard_lite_out(den_hi) : ni_guard_out(guard)) | ni_sqrt_out(ms);
     en = ni_sqrt_core(ms);
     pw = ni_pow_ctrl_ms<Tab::ORDER + 1>(ms, en);
     en_lt1 = (unsigned)__double2hiint(en) < 0x3ff00000u;  // en > 0 here
@@ -988,6 +998,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
   long long idx = 0;
   bool active = false, exhausted = false, svc = true;
   double t = 0, h_abs = 0, tb = 0, dir = 1, tn = 0, step_h = 0;
+  double hs = 0;  // the signed step of the coming attempt, +-h_abs: carried from the step entry to the attempt
   double y[n], kl[n], p[P > 0 ? P : 1];
 #pragma unroll
   for (int i = 0; i < n; ++i) y[i] = kl[i] = 0.0;
@@ -1158,13 +1169,15 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         const bool same = (__double2hiint(dtb) ^ __double2hiint(dir)) >= 0;
         if (zero || same) {  // direction * (t_new - t_bound) >= 0: this attempt ends on t_bound
           tn = tb;
-          // (the clipped step t_bound - t has the sign of `direction`: h below is again +-h_abs)
+          // (the clipped step t_bound - t has the sign of `direction`: the step is again +-h_abs)
           h_abs = fabs(__dadd_rn(tn, -t));
         }
+        hs = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs)) : h_abs;
       } else {
         // a lane without work keeps executing the arithmetic: give it values that raise no flag
         t = 0.0;
         h_abs = 0.0;
+        hs = 0.0;
         tn = 0.0;
         tb = 0.0;
         kx = 0;
@@ -1177,12 +1190,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     // ================================================================ HOT: one attempt for every lane
     // h = h_abs * direction (_advanced.py:163; a sign flip: direction = +-1) or h_abs (_basic.py:148); also after a
     // clip to t_bound, where h_abs = |t_bound - t|
-    const double h = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
-                         : h_abs;
+    const double h = hs;
     double en, pw, kn[n], yn[n], auxn[Q > 0 ? Q : 1], num[n];
     bool ok;
     unsigned out;
-    ni_rk_attempt<Rhs, METHOD, FAST>(a, t, tn, h, y, kl, p, yn, kn, auxn, num, en, pw, ok, out);
+    ni_rk_attempt<Rhs, METHOD, FAST, true>(a, t, tn, h, y, kl, p, yn, kn, auxn, num, en, pw, ok, out);
     if constexpr (FAST) {
       // (en holds the mean square error) the root without its range checks; outside [2^-100, 2^100) or NaN: cold block
       pw = ni_pow_fast_core<2 * (Tab::ORDER + 1)>(en);
@@ -1259,9 +1271,8 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     // trajectory, 0.2 % of the lane-attempts); the 8 ulp floor of a step entry (:139-143) is the service branch's, which
     // the cold block requests.  A trajectory whose last step ended on t_bound asks for the service branch here.
     {
-      const double hn = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs))
-                            : h_abs;
-      tn = __dadd_rn(t, hn);
+      hs = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs)) : h_abs;
+      tn = __dadd_rn(t, hs);
       svc = REC ? (cold | (rc_len - rc_off < 32)) : cold;
       if ((__double2hiint(tn) ^ kx) >= tbk) {
         if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // (:135) t_bound has been reached: the trajectory leaves
@@ -1274,6 +1285,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
             tn = tb;
             // (the clipped step t_bound - t has the sign of `direction`: the next h is again +-h_abs)
             h_abs = fabs(__dadd_rn(tn, -t));
+            hs = ADV ? __hiloint2double(__double2hiint(h_abs) ^ (__double2hiint(dir) & (int)0x80000000), __double2loint(h_abs)) : h_abs;
           }
         }
       }
@@ -1290,7 +1302,7 @@ NI_DEV void ni_small_run_body(const NiArgs &a) {
   if constexpr (NI_LEAN && SEM != 2 && NI_COND == 0) {
     // fast-forward without an attempt budget and with max_step = inf (recording: chunked slot reservation, i.e. an
     // ensemble of at least 65 536 trajectories); lock-step ni.step and everything else take the general body
-    if (no_max_step && a.max_attempts >= 0x7fffffffLL && a.max_accepts >= 0x7fffffffLL && (!REC || a.rec_chunk >= 32))
+    if (no_max_step && a.atol_floor && a.max_attempts >= 0x7fffffffLL && a.max_accepts >= 0x7fffffffLL && (!REC || a.rec_chunk >= 32))
       ni_small_run_lean<Rhs, METHOD, SEM == 1, FAST, REC>(a);
     else
       ni_small_run_impl<Rhs, METHOD, SEM, REC, FAST, true>(a);

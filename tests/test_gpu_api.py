@@ -522,6 +522,13 @@ def test_branch_free_tail_arithmetic_matches_the_operators():
     for which in (2, 3):
         _lib.check(L.ni_devmath_check(0, which, n, 99 + which, ctypes.byref(bad)))
         assert 0 <= bad.value <= n * 5e-5, (which, bad.value)
+    # the lean body's guard: scales up to 2^1020, any error
+    _lib.check(L.ni_devmath_check(0, 5, n, 4321, ctypes.byref(bad)))
+    assert bad.value == 0, bad.value
+    # the reciprocal behind the quotient: |1 - b r| <= 2^-52 (so a quotient can only be misrounded when the exact value
+    # lies within ~2^-104 relative of a rounding boundary: ~2^-50 of all operand pairs)
+    _lib.check(L.ni_devmath_check(0, 4, n, 77, ctypes.byref(bad)))
+    assert 0 < bad.value <= 2 ** 12, bad.value
 
 
 def test_long_lock_step_loop_uses_the_graph_path_and_matches_fast_forward():
