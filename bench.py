@@ -215,7 +215,7 @@ def main():
     N, n = w.N, w.n
     f = ni.BuiltinRHS(w.rhs)
     record = args.workload == 'c2' or args.record
-    rec_per_traj = {'c2': 1000, 'c3': 620, 'c4': 5200, 'c5': 260}[args.workload]  # accepted steps per trajectory, with headroom
+    rec_per_traj = {'c2': 1000, 'c3': 620, 'c4': 5200, 'c5': 160}[args.workload]  # accepted steps per trajectory, with headroom
 
     def build_ensemble(wk=None, arithmetic=None):
         wk = wk or w

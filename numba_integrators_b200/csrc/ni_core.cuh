@@ -1206,15 +1206,18 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     // MIN_FACTOR, a rejected one <= 0.9 < MAX_FACTOR), on the integer pipe: 10.0 has a zero low word, so
     // sp >= 10 <=> hi(sp) >= hi(10); sp < 0.2 is a 64-bit integer compare of non-negative doubles
     const double sp = __dmul_rn(NI_MC(0, 0.9), pw);
-    double fac = __double2hiint(sp) >= 0x40240000 ? 10.0 : sp;
+    // (both clamps stay in line: the first rejection after the ten-fold growth from a small initial step usually has
+    // an error norm above 1845, i.e. MIN_FACTOR -- sending it to the cold block cost C3 3 %)
+    double fac = (unsigned)__double2hiint(sp) >= 0x40240000u ? 10.0 : sp;
     fac = ni_lt_pos(fac, 0.2) ? 0.2 : fac;
     double h_new = __dmul_rn(h_abs, fac);
     // Lanes that need the cold block commit there; the hot commit below runs on predicates that never leave the
-    // predicate registers (a flag merged across the cold call is materialised as a byte: six more instructions)
-    // (bitwise, not short-circuit: nvcc otherwise threads the `active` test through the clamps above and duplicates them)
-    const bool rare = active & ((out != 0u) | ((unsigned)__double2hiint(h_new) < (unsigned)xs));
+    // predicate registers (a flag merged across the cold call is materialised as a byte: six more instructions).
+    // Lanes without work may raise `rare` (their benign values give a zero error): they take the branch and skip the
+    // call -- testing `active` up here cost two instructions in every pass, the detour only costs the tail of a run.
+    const bool rare = (out != 0u) | ((unsigned)__double2hiint(h_new) < (unsigned)xs);
     bool cold = false, cold_acc = false;
-    if (rare) {
+    if (rare && active) {
       NiLeanColdIn<n> v;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
@@ -1222,7 +1225,8 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         v.y[i] = y[i];
         v.yn[i] = yn[i];
       }
-      const NiLeanCold c = ni_lean_cold<n, METHOD, FAST>(v, a.rtol, a.atol, t, dir, h_abs, en, pw, ok ? 1 : 0, out);
+      // (|h| is the h_abs this attempt started from: passing h keeps the old h_abs dead after the multiply above)
+      const NiLeanCold c = ni_lean_cold<n, METHOD, FAST>(v, a.rtol, a.atol, t, dir, fabs(h), en, pw, ok ? 1 : 0, out);
       h_new = c.h_new;
       if (c.flags & 5) {  // accepted, or the failure exit: commit the attempt (the rejected t, y when failing)
         t = tn;
@@ -1248,7 +1252,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
       kl[i] = kn[i];  // also after a rejection: the stale FSAL stage
     }
     h_abs = h_new;
-    if (take) ++nacc;
+    nacc += take ? 1 : 0;
     ++iter;
     if constexpr (REC) {
       // one slot per accepting lane, handed out by ballot rank: consecutive lanes write consecutive slots

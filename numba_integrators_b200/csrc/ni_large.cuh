@@ -354,6 +354,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       long long idx = (long long)atomicAdd(a.queue, 1ull);
       if (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW)) idx = a.N;
       c.bcast[0] = idx;
+      if (REC) c.bcast[3] = c.bcast[4] = c.bcast[5] = 0;  // this trajectory holds no record slots yet
     }
     __syncthreads();
     const long long idx = c.bcast[0];
@@ -386,6 +387,15 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     bool last_accept = false, fresh = true, done = false;
     bool srej = SP ? a.step_rejected[idx] != 0 : false;  // scipy: a rejection happened in the current step
     double eps = 0, min_step = 0;
+    // REC: record slots are reserved in chunks of `rec_k` per trajectory (one atomicAdd + two barriers per chunk instead
+    // of per accepted step) and live in shared memory: bcast[3] / bcast[5] = the next free slot, read by the even / odd
+    // accepted steps (thread 0 writes the entry the NEXT step reads, so no thread can see a half-updated one), bcast[4]
+    // = end of the chunk.  An attempt only starts with a slot in hand, so an accepted step always has its row and a
+    // full log stops the trajectory BETWEEN attempts: nothing is undone, nothing extra stays live across the attempt
+    // (the kernel runs at the 255-register limit: two more live values were 100 bytes of spills and 25 % of C5).
+    // Slots left over when the trajectory leaves are tagged NI_REC_INVALID; the drain skips them.
+    const long long rec_k = a.max_accepts >= 0x7fffffffLL ? 8 : 1;
+    bool log_full = false;
 
     while (!done) {
       if (fresh) {  // step entry (_basic.py:135-143)
@@ -404,8 +414,28 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         }
         fresh = false;
       }
+      if constexpr (REC) {
+        __syncthreads();  // thread 0's update of the slot entries at the last accepted step
+        const int rp = 3 + 2 * (nacc & 1);
+        long long s_next = c.bcast[rp];
+        if (s_next >= c.bcast[4]) {  // (uniform) a new chunk
+          __syncthreads();
+          if (tid == 0) {
+            const long long base = (long long)atomicAdd(a.rec_cursor, (unsigned long long)rec_k);
+            c.bcast[rp] = base;
+            c.bcast[4] = base + rec_k;
+          }
+          __syncthreads();
+          s_next = c.bcast[rp];
+        }
+        if (s_next >= a.rec_cap) {  // the log is full: the trajectory waits for the drain (still RUNNING)
+          if (tid == 0) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+          log_full = true;
+          last_accept = false;
+          break;
+        }
+      }
       // ---- one attempt (_basic.py:145-169)
-      const double h_pre = h_abs;
       if (SP && h_abs < min_step) {  // scipy tests the step size before every attempt and commits nothing
         status = NI_ST_FAILED;
         last_accept = false;
@@ -557,21 +587,16 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       --att_left;
 
       // ---- controller + commit: uniform across the CTA
-      bool park = false;
+      constexpr bool park = false;  // (record-log back-pressure acts before the attempt)
       long long slot = -1;
-      if (REC && ok) {
-        if (tid == 0) c.bcast[1] = (long long)atomicAdd(a.rec_cursor, 1ull);
-        __syncthreads();
-        slot = c.bcast[1];
-        park = slot >= a.rec_cap;
-      }
+      if (REC && ok) slot = c.bcast[3 + 2 * (nacc & 1)];
       const double sp = __dmul_rn(0.9, pw);
       double fac = ok ? (en == 0.0 ? 10.0 : fmin(10.0, sp)) : fmax(0.2, sp);
       if (SP && ok && srej) fac = fmin(1.0, fac);  // scipy: no growth in a step that saw a rejection
       const double h_new = __dmul_rn(h_abs, fac);
       const bool fail = !SP && !ok && !nan && h_new < min_step;
       const bool take = (ok && !park) || fail;
-      h_abs = park ? h_pre : (nan ? h_abs : h_new);
+      h_abs = nan ? h_abs : h_new;
       if (take) {
         t = tn;
 #pragma unroll
@@ -589,12 +614,37 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         ++nacc;
         --acc_left;
         if (REC) {
+          // The recorded row (32 776 B per step for n = 4096).  Stencil layout: a thread owns CPT consecutive components,
+          // so a store straight from the registers touches 32 different 128-byte lines per warp instruction and the
+          // load/store unit serialises them (measured on C5: recording cost 28 % of the run; 16-byte vectors did not
+          // help).  Each warp therefore transposes its 32 * CPT consecutive components through shared memory -- the stage
+          // slot is dead between the error norm and the next attempt's stage loop, an XOR swizzle keeps both passes free
+          // of bank conflicts, and only __syncwarp is needed -- and writes them with fully coalesced stores (two lines
+          // per instruction).  A bulk copy (cp.async.bulk) of the row would need the LINEAR image in shared memory, which
+          // is exactly the conflict-ridden pattern (lane stride CPT * 8 = 128 bytes).
+          if constexpr (!Rhs::COMPONENT && (CPT & (CPT - 1)) == 0) {
+            const int lane = tid & 31, w0 = (tid & ~31) * CPT;
+            double *const wb = c.vec + w0;
 #pragma unroll
-          for (int i = 0; i < CPT; ++i)
-            if (ni_large_j<Rhs>(c, i) < n) a.rec_y[slot * n + ni_large_j<Rhs>(c, i)] = y[i];
+            for (int i = 0; i < CPT; ++i) wb[lane * CPT + (i ^ (lane & (CPT - 1)))] = y[i];
+            __syncwarp();
+            double *const row = a.rec_y + slot * n + w0;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+              const int g = k * 32 + lane, r = g / CPT, i = g % CPT;
+              const double v = wb[r * CPT + (i ^ (r & (CPT - 1)))];
+              if (w0 + g < n) row[g] = v;
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+              if (ni_large_j<Rhs>(c, i) < n) a.rec_y[slot * n + ni_large_j<Rhs>(c, i)] = y[i];
+          }
           if (tid == 0) {
             a.rec_traj[slot] = (unsigned int)idx;
             a.rec_t[slot] = t;
+            c.bcast[3 + 2 * (nacc & 1)] = slot + 1;  // (nacc already counts this step: the entry the next one reads)
           }
         }
         if constexpr ((REC && Rhs::Q > 0) || NI_COND != 0) {
@@ -622,10 +672,6 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
       } else if (!park) {
         ++nrej;
       }
-      if (park) {
-        ++att_left;
-        if (tid == 0) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
-      }
       fresh = accepted;
       last_accept = accepted;
       if (fail) status = NI_ST_FAILED;
@@ -645,6 +691,11 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         done = true;
       }
     }
+    if (REC && tid == 0) {  // reserved, never used
+      const long long end = c.bcast[4] < a.rec_cap ? c.bcast[4] : a.rec_cap;
+      for (long long sl = c.bcast[3 + 2 * (nacc & 1)]; sl < end; ++sl) a.rec_traj[sl] = NI_REC_INVALID;
+    }
+    (void)log_full;
     // ---- retire
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {

@@ -84,3 +84,51 @@ def test_per_trajectory_step_limits_on_a_large_system():
     assert np.array_equal(s.n_accepted, g['n_accepted']) and np.array_equal(s.n_rejected, g['n_rejected'])
     assert np.array_equal(s.nfev, g['nfev'])
     assert np.allclose(s.y, g['y'], rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize('n', [200, 333])
+def test_recording_on_cta_per_trajectory_kernels(n):
+    """The record log of the large kernels (32 776 B per step at n = 4096): every accepted (t, y) of a fast-forward run
+    equals the lock-step sequence of a single solver bit for bit; the record slot is reserved one step ahead (the last
+    step of a trajectory reserves none, so no slot is wasted); a log that is too small stops the trajectories between
+    attempts, and draining + relaunching loses nothing."""
+    from numba_integrators_b200 import workloads as wl
+    h = wl.c5_heat(N=24, n=n, t_bound=1.0)
+    make = lambda **kw: ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 1.0, rtol=1e-8, atol=1e-8, **kw)
+    ens = make(record=20_000)
+    assert ens.run() == 0
+    total = int(ens.n_accepted.sum())
+    assert ens.record_count() == total
+    rec = ens.record_drain().sorted()
+    assert len(rec) == total
+    for k in (0, 7, 23):
+        one = ni.RK45(ni.rhs.heat1d(h.params[k, 0]), 0.0, h.y0[k], 1.0, rtol=1e-8, atol=1e-8)
+        ts, ys = [], []
+        while ni.step(one):
+            ts.append(one.t)
+            ys.append(one.y)
+        tk, yk, _ = rec.trajectory(k)
+        assert np.array_equal(tk, np.array(ts)) and np.array_equal(yk, np.array(ys))
+    # a log that is too small: drain and continue
+    small = make(record=300)
+    got = []
+    for _ in range(200):
+        try:
+            small.run()
+            got.append(small.record_drain())
+            break
+        except ni.NiError as e:
+            assert e.code == -6
+            got.append(small.record_drain())
+    assert sum(len(g) for g in got) == total
+    assert np.array_equal(small.y, ens.y) and np.array_equal(small.n_accepted, ens.n_accepted)
+    assert np.array_equal(small.n_rejected, ens.n_rejected)
+    # lock-step recording: one slot per accepted step, nothing wasted
+    lock = make(record=20_000)
+    while ni.step(lock):
+        pass
+    assert lock.record_count() == total
+    lrec = lock.record_drain().sorted()
+    t7, y7, _ = lrec.trajectory(7)
+    r7 = rec.trajectory(7)
+    assert np.array_equal(t7, r7[0]) and np.array_equal(y7, r7[1])

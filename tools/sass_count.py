@@ -1,13 +1,17 @@
-"""Static instruction and register-operand counts of the run kernels' hot loops, read off the SASS with cuobjdump.
+"""Static instruction, register-operand and register-port counts of the run kernels' hot loops, read off the SASS.
 
-The thread-per-trajectory run kernel is bound by register-file read bandwidth (DESIGN.md section 3.2,
-profiles/r02_issue_model.txt: a scheduler reads two 32-bit register operands per lane per cycle, and an FP64 instruction
-with two 64-bit register sources uses that for both of its pipe cycles).  This script prints, for one pass through the
-hot loop -- everything between the loop's EXIT test and its back edge, minus the cold regions (forward-skipped spans that
-contain a CALL or an FP64 compare: the operator slow paths, the lean body's cold block and its rare clip to t_bound) -- D = FP64-pipe instructions, I = all others, and
-R = 32-bit register source operands read (64-bit operands count twice, operands served by the reuse cache not at all):
-one attempt costs about max(2 D, R / 2) scheduler cycles.  Every loop body of a kernel is listed (ni_small_run_body
-carries two: the lean one and the general one).
+The thread-per-trajectory run kernel is bound by the register file's read ports (DESIGN.md section 3.2,
+profiles/r02_port_model.txt).  This script prints, for one pass through the hot loop -- everything between the loop's
+EXIT test and its back edge, minus the cold regions (forward-skipped spans that contain a CALL, a shared-memory store or
+an FP64 compare: the operator slow paths, the cold block, the rare clip to t_bound) --
+  D = FP64-pipe instructions, I = all others,
+  R = 32-bit register source operands read (64-bit operands count twice, reuse-cache hits not at all),
+  port cycles = sum over the instructions of max(1, distinct even-numbered sources, distinct odd-numbered sources):
+      a scheduler's register file has two banks (register number mod 2), each delivers one 32-bit register per lane
+      per cycle; a 64-bit operand is one read in each bank.  Measured kernel time per warp-pass per scheduler is
+      1.00 - 1.06 x this number for C2, C3, C4 and four variants of C3 (it replaces round 1's `2 D + I` and the bank-blind
+      `1.18 x R / 2`).
+Every loop body of a kernel is listed (ni_small_run_body carries two: the lean one and the general one).
 
     python tools/sass_count.py [object [mangled kernel name]]
 """
