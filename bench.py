@@ -310,11 +310,49 @@ def main():
             best = tmax if best is None else min(best, tmax)
         return best, g.dtype.itemsize
 
-    gather_ms, strong = None, None
+    def timed_fused(e, n_global, interleaved, acc_total):
+        """Steps with the gather fused into the integration (distributed.FusedGather): the run kernel stores every
+        finished trajectory's terminal record to all GPUs' receive buffers while it integrates; the step ends with the
+        barrier that makes them visible.  -> whole step incl. gather, ms (max over ranks), or None without peer memory."""
+        from numba_integrators_b200 import distributed as nd
+        if e.kind:  # CTA-per-trajectory kernels have no in-kernel sink
+            return None
+        g = nd.FusedGather(e, n_global, interleaved)
+        if g.hdl is None:
+            g.close()
+            return None
+        for _ in range(max(1, args.warmup)):
+            e.reset()
+            g.begin()
+            e.run_async()
+            g.finish()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record()
+        for _ in range(args.steps):
+            e.reset()
+            g.begin()
+            e.run_async()
+            g.finish()
+        f1.record()
+        barrier()
+        ms_f = reduce_max(f0.elapsed_time(f1)) / args.steps
+        st = e.status
+        assert np.all(st == _lib.ST_FINISHED)
+        rows = g.recv.view(world, -1)[rank][:e.N * g.dtype.itemsize].cpu().numpy().view(g.dtype)
+        assert np.array_equal(rows['n_accepted'], e.n_accepted) and np.array_equal(rows['t'], e.t)  # own slot, spot check
+        impl = g.impl
+        g.close()
+        return {'ms_per_step_incl_gather': ms_f, 'value_incl_gather': acc_total / (ms_f * 1e-3), 'impl': impl,
+                'record_bytes': g.dtype.itemsize}
+
+    gather_ms, strong, fused = None, None, None
     if world > 1:
         gather_nccl_ms, rec_bytes = timed_gather(ens, N * world, False)
         gather_peer_ms, _ = timed_gather(ens, N * world, False, peer=True)
         gather_ms = min(x for x in (gather_nccl_ms, gather_peer_ms) if x is not None)
+        fused = timed_fused(ens, N * world, False, acc_all)
         # ---- strong scaling: the single-GPU problem (--traj trajectories IN TOTAL) sharded over the GPUs
         from numba_integrators_b200 import distributed as nd
         from numba_integrators_b200.workloads import Workload
@@ -346,6 +384,10 @@ def main():
                   'note': 'the same trajectories a 1-GPU run integrates, sharded by index; efficiency = strong rate / '
                           '(weak whole-job rate, i.e. n_gpus x the per-GPU rate at full occupancy)'}
         strong['_fp64_flops'] = ws.flops_per_attempt * s_att_all  # -> frac below, once the peak is known
+        s_fused = timed_fused(ens_s, args.traj, inter, s_acc_all)
+        if s_fused is not None:
+            s_fused['efficiency_vs_weak_incl_gather'] = s_fused['value_incl_gather'] / value
+            strong['fused_gather'] = s_fused
         del ens_s
 
     # ---- end to end through the C ABI with pinned host buffers
@@ -489,6 +531,11 @@ def main():
             line['ms_incl_gather'] = step_ms + gather_ms
             line['value_incl_gather'] = acc_all / ((step_ms + gather_ms) * 1e-3)
             line['gather_GBps_per_rank'] = rec_bytes * N * (world - 1) / (gather_ms * 1e-3) / 1e9
+            if fused is not None:
+                # the gather fused into the integration: the run kernel stores the terminal records to every GPU while
+                # it integrates; the figure is a whole step INCLUDING the gather
+                fused['efficiency_vs_value'] = fused['value_incl_gather'] / value
+                line['fused_gather'] = fused
         if strong is not None:
             strong['frac'] = strong.pop('_fp64_flops') / world / (strong['run_kernel_ms_max_over_ranks'] * 1e-3) / 1e12 / fp64_peak
             line['strong'] = strong

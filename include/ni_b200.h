@@ -217,6 +217,15 @@ int ni_ensemble_get_terminal(ni_ensemble *e, void *host_out);
  * peers' buffers, e.g. torch.distributed._symmetric_memory, and synchronises the GPUs afterwards).  The transfer
  * overlaps the packing; no staging copy and no library collective on the path. */
 int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_device, int n_dst);
+/* The gather fused into the INTEGRATION (thread-per-trajectory kernels): with a sink set, every trajectory that leaves
+ * a run kernel for good (finished, failed, non-finite; also one that was finished before the launch) stores its terminal
+ * record -- the packed record above, zero-padded to a multiple of 16 bytes: ni_ensemble_terminal_sink_bytes, 64 for
+ * Lorenz-63 -- to row first_row + i of each of the n_dst (<= 8) device buffers, as 16-byte vectors.  The buffers are this
+ * GPU's slot in the receive buffer of every GPU of the job (peer memory over NVLink / NVSwitch, mapped by the caller):
+ * the one collective of the path (reference: none -- single process) then costs a barrier after the run,
+ * not a transfer.  n_dst = 0 switches the sink off.  The setting is part of the launch arguments of every later run. */
+int ni_ensemble_terminal_sink_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory);
+int ni_ensemble_set_terminal_sink(ni_ensemble *e, void *const *dst_device, int n_dst, int64_t first_row);
 
 
 /* ---- recording of accepted steps into an HBM append log --------------------------------

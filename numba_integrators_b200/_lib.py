@@ -65,6 +65,8 @@ SIGNATURES = {
     'ni_ensemble_pack_terminal': (C.c_int, [_vp, _vp]),
     'ni_ensemble_get_terminal': (C.c_int, [_vp, _vp]),
     'ni_ensemble_pack_terminal_peers': (C.c_int, [_vp, C.POINTER(_vp), C.c_int]),
+    'ni_ensemble_terminal_sink_bytes': (C.c_int, [_vp, _i64p]),
+    'ni_ensemble_set_terminal_sink': (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int64]),
     'ni_ensemble_record_enable': (C.c_int, [_vp, C.c_int64]),
     'ni_ensemble_record_count': (C.c_int, [_vp, _i64p]),
     'ni_ensemble_record_drain': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i64p]),

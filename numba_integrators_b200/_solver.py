@@ -444,6 +444,23 @@ class Ensemble:
         arr = (_lib._vp * len(dst_device_ptrs))(*[int(p) for p in dst_device_ptrs])
         check(self._L.ni_ensemble_pack_terminal_peers(self._h, arr, len(dst_device_ptrs)))
 
+    def terminal_sink_dtype(self):
+        """numpy dtype of one row of an in-kernel terminal sink: the fields of terminal_dtype(), rows padded to a multiple
+        of 16 bytes (ni_ensemble_terminal_sink_bytes: 64 for Lorenz-63)."""
+        b = C.c_int64(0)
+        check(self._L.ni_ensemble_terminal_sink_bytes(self._h, b))
+        dt = self.terminal_dtype()
+        return np.dtype({'names': list(dt.names), 'formats': [dt.fields[k][0] for k in dt.names],
+                         'offsets': [dt.fields[k][1] for k in dt.names], 'itemsize': b.value})
+
+    def set_terminal_sink(self, dst_device_ptrs, first_row=0):
+        """The gather fused into the integration: from now on every trajectory that leaves a run kernel for good stores
+        its terminal record (terminal_sink_dtype()) to row first_row + i of every buffer of `dst_device_ptrs` (device
+        memory of this or of peer GPUs; up to 8).  An empty list switches the sink off."""
+        ptrs = [int(p) for p in dst_device_ptrs]
+        arr = (_lib._vp * max(1, len(ptrs)))(*ptrs)
+        check(self._L.ni_ensemble_set_terminal_sink(self._h, arr, len(ptrs), int(first_row)))
+
     def terminal(self):
         """The terminal records on the host: structured array (t, y, aux, n_accepted, n_rejected, status), one D2H copy."""
         out = np.empty(self.N, dtype=self.terminal_dtype())

@@ -1479,6 +1479,26 @@ NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_t
   return NI_OK;
 }
 
+NI_API int ni_ensemble_terminal_sink_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory) {
+  if (!e || !bytes_per_trajectory) return fail(NI_ERR_INVALID, "ensemble / bytes_per_trajectory is NULL");
+  *bytes_per_trajectory = 16 * (int64_t)ni_sink_vectors(e->mod.n, e->mod.Q);
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_set_terminal_sink(ni_ensemble *e, void *const *dst_device, int n_dst, int64_t first_row) {
+  if (!e || n_dst < 0 || n_dst > NI_SINK_MAX || (n_dst > 0 && !dst_device) || first_row < 0)
+    return fail(NI_ERR_INVALID, "need an ensemble, 0..%d destination buffers and a first row >= 0", NI_SINK_MAX);
+  if (n_dst > 0 && e->mod.kind != NI_KIND_SMALL)
+    return fail(NI_ERR_UNSUPPORTED, "the in-kernel terminal sink belongs to the thread-per-trajectory kernels "
+                                    "(CTA-per-trajectory systems: ni_ensemble_pack_terminal_peers after the run)");
+  for (int r = 0; r < n_dst; ++r)
+    if (!dst_device[r] || ((uintptr_t)dst_device[r] & 15)) return fail(NI_ERR_INVALID, "destination %d is NULL or not 16-byte aligned", r);
+  for (int r = 0; r < NI_SINK_MAX; ++r) e->a.sink[r] = r < n_dst ? (unsigned int *)dst_device[r] : nullptr;
+  e->a.sink_n = n_dst;
+  e->a.sink_row0 = first_row;
+  return NI_OK;
+}
+
 NI_API int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_device, int n_dst);
 NI_API int ni_ensemble_pack_terminal(ni_ensemble *e, void *dst_device) {
   if (!e || !dst_device) return fail(NI_ERR_INVALID, "ensemble / dst_device is NULL");

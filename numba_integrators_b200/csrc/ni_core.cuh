@@ -57,6 +57,7 @@
 #define NI_LEAN 1  // 0: every launch takes the general run body (A/B experiments)
 #endif
 
+#define NI_SINK_MAX 8  // destinations of the in-kernel terminal sink (the GPUs of one box)
 #define NI_FLAG_REC_OVERFLOW 1ull
 #define NI_REC_INVALID 0xffffffffu  // rec_traj value of a reserved-but-unused record slot
 
@@ -108,6 +109,13 @@ struct NiArgs {
   unsigned int *rec_traj;       // trajectory of the record in a slot (NI_REC_INVALID: reserved, never written); the step
                                 // number is not stored: the records of one trajectory appear in step order
   double *rec_t, *rec_y, *rec_aux;  // rec_y [n][rec_cap], rec_aux [Q][rec_cap]
+  // terminal sink (thread-per-trajectory kernels): a trajectory that leaves the run kernel for good also stores its
+  // packed terminal record (t, y, aux, n_accepted, n_rejected, status; padded to 16-byte vectors) to row
+  // sink_row0 + idx of up to NI_SINK_MAX device buffers -- this GPU's slot in the receive buffer of every GPU of the
+  // job, peer memory over NVLink: the final gather overlaps the integration instead of following it
+  unsigned int *sink[NI_SINK_MAX];
+  int sink_n;                   // 0: no sink
+  long long sink_row0;
   // ff2cond: built-in predicate parameters
   int cond_kind;                // 0: no predicate; != 0: ff2cond launch of a kernel compiled with a predicate
   int cond_index;
@@ -119,6 +127,40 @@ struct NiArgs {
 // max_step / first_step of trajectory idx (_basic.py:292-299: per-object arguments of the reference's factories)
 NI_DEV double ni_max_step(const NiArgs &a, long long idx) { return a.max_step_v ? a.max_step_v[idx] : a.max_step; }
 NI_DEV double ni_first_step(const NiArgs &a, long long idx) { return a.first_step_v ? a.first_step_v[idx] : a.first_step; }
+
+// 16-byte vectors of one terminal-sink row: the packed record of include/ni_b200.h (2 (1 + n + Q) + 3 words), padded
+NI_HD constexpr int ni_sink_vectors(int n, int Q) { return (2 * (1 + n + Q) + 3 + 3) / 4; }
+// The terminal record of trajectory idx -- read back from the state arrays its lane has just written (or that the
+// init kernel wrote, for a trajectory that was finished before the launch) -- to every sink buffer.  Rare path.
+template <int n, int Q>
+NI_DEV void ni_sink_write(const NiArgs &a, long long idx) {
+  if (a.sink_n <= 0) return;
+  constexpr int DW = 2 * (1 + n + Q), V = ni_sink_vectors(n, Q);
+  unsigned w[V * 4];
+#pragma unroll
+  for (int k = 0; k < V * 4; ++k) w[k] = 0u;
+  auto put = [&](int c, double v) {
+    w[2 * c] = (unsigned)__double2loint(v);
+    w[2 * c + 1] = (unsigned)__double2hiint(v);
+  };
+  put(0, a.t[idx]);
+#pragma unroll
+  for (int i = 0; i < n; ++i) put(1 + i, a.y[i * a.N + idx]);
+#pragma unroll
+  for (int i = 0; i < Q; ++i) put(1 + n + i, a.aux[i * a.N + idx]);
+  w[DW] = (unsigned)a.n_acc[idx];
+  w[DW + 1] = (unsigned)a.n_rej[idx];
+  w[DW + 2] = (unsigned)a.status[idx];
+  // (unrolled over the destinations: a run-time index into the kernel arguments would copy them to local memory)
+#pragma unroll
+  for (int r = 0; r < NI_SINK_MAX; ++r) {
+    if (r < a.sink_n) {
+      uint4 *dst = reinterpret_cast<uint4 *>(a.sink[r]) + (a.sink_row0 + idx) * V;
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+  }
+}
 
 // Arithmetic policy.  Strict (FAST = false): every element-wise expression is evaluated unfused, as numba
 // evaluates it in the reference (bit-identical results).  Fast: multiply-adds are
@@ -679,6 +721,7 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
           }
           if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
           if (last_accept) atomicAdd(a.queue + 3, 1ull);
+          if (status != NI_ST_RUNNING) ni_sink_write<n, Q>(a, idx);
           active = false;
         }
         // refill: pop trajectories (warp-aggregated) until one is runnable or the queue is empty
@@ -697,7 +740,10 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
           status = a.status[idx];
           if (COND && a.cond_hit[idx]) status = -1;  // ff2cond: already stopped at its predicate
           if (status != NI_ST_RUNNING) {
-            if (status >= 0) a.running[idx] = 0;  // step() on a finished / failed solver returns False
+            if (status >= 0) {
+              a.running[idx] = 0;  // step() on a finished / failed solver returns False
+              ni_sink_write<n, Q>(a, idx);
+            }
             continue;
           }
           t = a.t[idx];
@@ -708,6 +754,7 @@ NI_DEV void ni_small_run_impl(const NiArgs &a) {
             a.step_size[idx] = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
             a.status[idx] = NI_ST_FINISHED;
             a.running[idx] = 0;
+            ni_sink_write<n, Q>(a, idx);
             continue;
           }
           step_h = a.step_size[idx];
@@ -1056,6 +1103,7 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         if (parking) a.park_list[atomicAdd(a.queue + 4, 1ull)] = (unsigned int)idx;
         if (mode == 2) atomicAdd(a.queue + 2, 1ull);
         if (status >= NI_ST_FAILED) atomicAdd(a.queue + 5, 1ull);
+        if (status != NI_ST_RUNNING) ni_sink_write<n, Q>(a, idx);
         active = false;
   };
 
@@ -1097,12 +1145,14 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
         for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
         if (status != NI_ST_RUNNING) {
           a.running[idx] = 0;  // step() on a finished / failed solver returns False
+          ni_sink_write<n, Q>(a, idx);
           continue;
         }
         if (__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) {  // t_bound has been reached (_basic.py:135-136)
           a.step_size[idx] = ADV ? h_abs : __dmul_rn(dir, h_abs);  // _advanced.py:151 / _basic.py:136
           a.status[idx] = NI_ST_FINISHED;
           a.running[idx] = 0;
+          ni_sink_write<n, Q>(a, idx);
           continue;
         }
         // reach key of this trajectory: hi(tn) ^ kx is monotone in dir * tn over the sign regime in which t_bound can

@@ -89,11 +89,13 @@ struct NiLargeSlots {
 
 // dynamic shared memory of one CTA, in doubles.  Stage vectors are laid out [slot][component][NI_LARGE_MAX_THREADS]
 // whatever the CTA size, so that every access is `thread base + immediate offset`.
-// Component right-hand sides (dense coupling) additionally stage the whole stage vector: + threads * cpt doubles.
+// Component right-hand sides (dense coupling) additionally stage the whole stage vector: + threads * cpt doubles;
+// stencil kernels carry a padded buffer of MAX_THREADS * (cpt + 1) doubles in which a warp transposes its part of a
+// recorded row (the record log wants coalesced stores, the registers hold cpt consecutive components per thread).
 NI_HD constexpr size_t ni_large_smem_doubles(int method, int threads, int cpt, bool component = false) {
   return (size_t)(method == NI_RK45 ? NiLargeSlots<NI_RK45>::TOTAL : NiLargeSlots<NI_RK23>::TOTAL) *
              NI_LARGE_MAX_THREADS * cpt + 4 * (size_t)NI_LARGE_MAX_THREADS + 2 * 32 + 8 +
-         (component ? (size_t)threads * cpt : 0);
+         (component ? (size_t)threads * cpt : (size_t)NI_LARGE_MAX_THREADS * (cpt + 1));
 }
 
 struct NiLargeCtx {
@@ -101,7 +103,8 @@ struct NiLargeCtx {
   double *edge;   // [2 parity][2 sides][T]
   double *part;   // [2 parity][32] per-warp partial sums
   long long *bcast;
-  double *ys;     // component right-hand sides only: the full stage vector [n]
+  double *ys;     // component right-hand sides only: the full stage vector [n]; stencil kernels: the transposition
+                  // buffer of recorded rows, [warp][32][cpt + 1]
   int T, tid, n, j0;
   bool full;  // n == T * CPT: no padding components, masks are skipped
 };
@@ -387,15 +390,37 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     bool last_accept = false, fresh = true, done = false;
     bool srej = SP ? a.step_rejected[idx] != 0 : false;  // scipy: a rejection happened in the current step
     double eps = 0, min_step = 0;
-    // REC: record slots are reserved in chunks of `rec_k` per trajectory (one atomicAdd + two barriers per chunk instead
-    // of per accepted step) and live in shared memory: bcast[3] / bcast[5] = the next free slot, read by the even / odd
-    // accepted steps (thread 0 writes the entry the NEXT step reads, so no thread can see a half-updated one), bcast[4]
-    // = end of the chunk.  An attempt only starts with a slot in hand, so an accepted step always has its row and a
-    // full log stops the trajectory BETWEEN attempts: nothing is undone, nothing extra stays live across the attempt
-    // (the kernel runs at the 255-register limit: two more live values were 100 bytes of spills and 25 % of C5).
-    // Slots left over when the trajectory leaves are tagged NI_REC_INVALID; the drain skips them.
-    const long long rec_k = a.max_accepts >= 0x7fffffffLL ? 8 : 1;
-    bool log_full = false;
+    // REC: record slots are reserved in chunks of 8 per trajectory (one atomicAdd per chunk instead of per accepted
+    // step; lock-step calls take one at a time) and live in shared memory: bcast[3] / bcast[5] = the next free slot,
+    // read by the even / odd accepted steps (thread 0 writes the entry the NEXT step reads, so no thread can see a
+    // half-updated one), bcast[4] = end of the chunk.  A trajectory only attempts a step with a slot in hand
+    // (`have_slot` here and after every accepted step), so an accepted step always has its row and a full log stops the
+    // trajectory BETWEEN attempts: nothing is undone and nothing extra stays live across the attempt (the kernel runs
+    // at the 255-register limit).  Slots left over when the trajectory leaves are tagged NI_REC_INVALID.
+    auto have_slot = [&]() -> bool {  // (uniform across the CTA)
+      __syncthreads();  // thread 0's update of the slot entries at the accepted step just recorded
+      const int rp = 3 + 2 * (nacc & 1);
+      long long s_next = c.bcast[rp];
+      if (s_next >= c.bcast[4]) {  // a new chunk
+        __syncthreads();
+        if (tid == 0) {
+          const long long k = a.max_accepts >= 0x7fffffffLL ? 8 : 1;
+          const long long base = (long long)atomicAdd(a.rec_cursor, (unsigned long long)k);
+          c.bcast[rp] = base;
+          c.bcast[4] = base + k;
+        }
+        __syncthreads();
+        s_next = c.bcast[rp];
+      }
+      if (s_next >= a.rec_cap) {  // the log is full: the trajectory waits for the drain (still RUNNING)
+        if (tid == 0) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
+        return false;
+      }
+      return true;
+    };
+    if constexpr (REC) {
+      if (!(__dmul_rn(dir, __dadd_rn(t, -tb)) >= 0.0) && !have_slot()) done = true;
+    }
 
     while (!done) {
       if (fresh) {  // step entry (_basic.py:135-143)
@@ -413,27 +438,6 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
           h_abs = min_step;
         }
         fresh = false;
-      }
-      if constexpr (REC) {
-        __syncthreads();  // thread 0's update of the slot entries at the last accepted step
-        const int rp = 3 + 2 * (nacc & 1);
-        long long s_next = c.bcast[rp];
-        if (s_next >= c.bcast[4]) {  // (uniform) a new chunk
-          __syncthreads();
-          if (tid == 0) {
-            const long long base = (long long)atomicAdd(a.rec_cursor, (unsigned long long)rec_k);
-            c.bcast[rp] = base;
-            c.bcast[4] = base + rec_k;
-          }
-          __syncthreads();
-          s_next = c.bcast[rp];
-        }
-        if (s_next >= a.rec_cap) {  // the log is full: the trajectory waits for the drain (still RUNNING)
-          if (tid == 0) atomicOr(a.queue + 1, NI_FLAG_REC_OVERFLOW);
-          log_full = true;
-          last_accept = false;
-          break;
-        }
       }
       // ---- one attempt (_basic.py:145-169)
       if (SP && h_abs < min_step) {  // scipy tests the step size before every attempt and commits nothing
@@ -615,25 +619,28 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         --acc_left;
         if (REC) {
           // The recorded row (32 776 B per step for n = 4096).  Stencil layout: a thread owns CPT consecutive components,
-          // so a store straight from the registers touches 32 different 128-byte lines per warp instruction and the
-          // load/store unit serialises them (measured on C5: recording cost 28 % of the run; 16-byte vectors did not
-          // help).  Each warp therefore transposes its 32 * CPT consecutive components through shared memory -- the stage
-          // slot is dead between the error norm and the next attempt's stage loop, an XOR swizzle keeps both passes free
-          // of bank conflicts, and only __syncwarp is needed -- and writes them with fully coalesced stores (two lines
-          // per instruction).  A bulk copy (cp.async.bulk) of the row would need the LINEAR image in shared memory, which
-          // is exactly the conflict-ridden pattern (lane stride CPT * 8 = 128 bytes).
-          if constexpr (!Rhs::COMPONENT && (CPT & (CPT - 1)) == 0) {
+          // so a store straight from the registers touches 32 different 128-byte lines per warp instruction.  Each warp
+          // transposes its 32 * CPT consecutive components through a padded shared-memory buffer ([lane][CPT + 1]:
+          // conflict-free both ways, every access is `per-lane base + immediate`, only __syncwarp is needed) and writes
+          // them with fully coalesced stores.  A bulk copy (cp.async.bulk) of the row would need the LINEAR image in
+          // shared memory, i.e. the conflict-ridden pattern (lane stride CPT * 8 = 128 bytes = all 32 banks).
+          if constexpr (!Rhs::COMPONENT) {
             const int lane = tid & 31, w0 = (tid & ~31) * CPT;
-            double *const wb = c.vec + w0;
+            double *const wb = c.ys + (tid >> 5) * (32 * (CPT + 1));
+            double *const wr = wb + lane * (CPT + 1);
 #pragma unroll
-            for (int i = 0; i < CPT; ++i) wb[lane * CPT + (i ^ (lane & (CPT - 1)))] = y[i];
+            for (int i = 0; i < CPT; ++i) wr[i] = y[i];
             __syncwarp();
-            double *const row = a.rec_y + slot * n + w0;
+            // element g = k * 32 + lane of the warp's chunk sits at [g / CPT][g % CPT]
+            const double *const rd = wb + (lane / CPT) * (CPT + 1) + lane % CPT;
+            double *const row = a.rec_y + slot * n + w0 + lane;
+            if (c.full) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-              const int g = k * 32 + lane, r = g / CPT, i = g % CPT;
-              const double v = wb[r * CPT + (i ^ (r & (CPT - 1)))];
-              if (w0 + g < n) row[g] = v;
+              for (int k = 0; k < CPT; ++k) row[k * 32] = rd[k * (32 / CPT) * (CPT + 1)];
+            } else {
+#pragma unroll
+              for (int k = 0; k < CPT; ++k)
+                if (w0 + k * 32 + lane < n) row[k * 32] = rd[k * (32 / CPT) * (CPT + 1)];
             }
             __syncwarp();
           } else {
@@ -690,12 +697,15 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
         last_accept = false;
         done = true;
       }
+      if constexpr (REC) {
+        if (accepted && !done && !have_slot()) done = true;  // (a full log: leave between two attempts)
+      }
     }
     if (REC && tid == 0) {  // reserved, never used
       const long long end = c.bcast[4] < a.rec_cap ? c.bcast[4] : a.rec_cap;
       for (long long sl = c.bcast[3 + 2 * (nacc & 1)]; sl < end; ++sl) a.rec_traj[sl] = NI_REC_INVALID;
     }
-    (void)log_full;
+
     // ---- retire
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {

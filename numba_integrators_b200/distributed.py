@@ -134,7 +134,7 @@ class PeerGather(TerminalGather):
         self.ens, self.N, self.interleaved, self.to_rank0 = ens, int(N_global), interleaved, False
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.dtype = ens.terminal_dtype()
+        self.dtype = self._record_dtype(ens)
         self.rows = shard_rows(self.N, self.world)
         own = len(shard_indices(self.N, self.rank, self.world, interleaved))
         if own != ens.N:
@@ -154,6 +154,10 @@ class PeerGather(TerminalGather):
             self.recv = torch.zeros((self.world, nbytes), dtype=torch.uint8, device=dev)
         self.send = self.recv[self.rank]
 
+    @staticmethod
+    def _record_dtype(ens):
+        return ens.terminal_dtype()
+
     @property
     def impl(self):
         return 'peer stores over NVLink (symmetric memory), fused with the packing kernel' if self.hdl is not None \
@@ -166,6 +170,49 @@ class PeerGather(TerminalGather):
         self.ens.pack_terminal_peers(self.dst)   # (the ensemble runs on torch's current stream, like the barriers)
         self.hdl.barrier()                       # every rank's stores have landed
         return self.recv
+
+
+class FusedGather(PeerGather):
+    """The gather fused into the INTEGRATION: the run kernel itself stores the terminal record of every trajectory
+    that finishes -- 64 bytes for Lorenz-63, four 16-byte vectors -- into this rank's slot of every rank's receive
+    buffer (ni_ensemble_set_terminal_sink; peer memory over NVLink / NVSwitch, mapped by symmetric memory).  The
+    transfer is spread over the whole run and hides behind the arithmetic; what is left of the collective is the
+    barrier after the run.  Usage: `g = FusedGather(ens, N); g.begin(); ens.run_async(); buf = g.finish()`.
+    Thread-per-trajectory kernels only.  Without symmetric memory the sink is this rank's own slot and `finish` runs
+    the NCCL collective."""
+
+    def __init__(self, ens, N_global, interleaved=False, group=None):
+        PeerGather.__init__(self, ens, N_global, interleaved, group)
+        ens.set_terminal_sink(self.dst if self.hdl is not None else [self.send.data_ptr()], 0)
+
+    @staticmethod
+    def _record_dtype(ens):
+        return ens.terminal_sink_dtype()
+
+    @property
+    def impl(self):
+        return 'peer stores over NVLink from the run kernel\'s retire path (symmetric memory): gather fused into the ' \
+               'integration' if self.hdl is not None else 'run kernel writes the local slot, NCCL all_gather_into_tensor'
+
+    def begin(self):
+        """Before the run: every rank is done reading the previous contents of the receive buffers."""
+        if self.hdl is not None:
+            self.hdl.barrier()
+
+    def finish(self):
+        """After the run (same stream): every rank's records have landed."""
+        import torch.distributed as dist
+        if self.hdl is not None:
+            self.hdl.barrier()
+        else:
+            dist.all_gather_into_tensor(self.recv.view(-1), self.send, group=self.group)
+        return self.recv
+
+    def run(self):
+        raise RuntimeError('FusedGather has no separate gather step: begin(), run the ensemble, finish()')
+
+    def close(self):
+        self.ens.set_terminal_sink([])
 
 
 def merge_records(recs, N, world, interleaved=False):

@@ -595,3 +595,53 @@ def test_state_fields_are_assignable_like_jitclass_attributes():
     d.t, d.y, d.h_abs, d.K = snap
     d.run()
     assert np.array_equal(d.y, c.y) and np.array_equal(d.n_accepted + 0, d.n_accepted)
+
+
+def test_terminal_sink_written_by_the_run_kernel():
+    """ni_ensemble_set_terminal_sink: the run kernel's retire path stores the packed terminal record of every trajectory
+    that leaves for good into every sink buffer (the gather fused into the integration: distributed.FusedGather).  The
+    rows must equal the records ni_ensemble_get_terminal packs afterwards -- lean body, general body (finite max_step),
+    lock-step calls, a trajectory that is already finished when the sink is set, and a failing trajectory."""
+    import torch
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c3_lorenz(N=3001, t_bound=1.0)
+    Solver = ni.Advanced(3, 1, ni.RK45)
+
+    def check(ens, first_row=0, drive=lambda e: e.run()):
+        dt = ens.terminal_sink_dtype()
+        assert dt.itemsize % 16 == 0 and dt.itemsize >= ens.terminal_dtype().itemsize and dt.names == ens.terminal_dtype().names
+        bufs = [torch.zeros((first_row + ens.N + 3) * dt.itemsize, dtype=torch.uint8, device='cuda') for _ in range(2)]
+        ens.set_terminal_sink([b.data_ptr() for b in bufs], first_row)
+        drive(ens)
+        ens.sync()
+        ref = ens.terminal()
+        for b in bufs:
+            rows = b.cpu().numpy().view(dt)
+            got = rows[first_row:first_row + ens.N]
+            for name in dt.names:
+                assert np.array_equal(got[name], ref[name], equal_nan=got[name].dtype.kind == 'f'), name
+            assert not rows[:first_row].view(np.uint8).any() and not rows[first_row + ens.N:].view(np.uint8).any()
+        ens.set_terminal_sink([])
+        return ref
+
+    a = check(Solver(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8), first_row=5)       # lean body
+    assert np.all(a['status'] == 1) and a['n_accepted'].min() > 20
+    b = check(Solver(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8, max_step=0.05))       # general body
+    assert np.all(b['n_accepted'] >= 20)
+
+    def lock_step(e):
+        while ni.step(e):
+            pass
+    c = check(Solver(ni.rhs.lorenz63, 0.0, w.y0[:200], w.params[:200], 0.2, rtol=1e-8, atol=1e-8), drive=lock_step)
+    assert np.all(c['t'] == 0.2)
+    done = Solver(ni.rhs.lorenz63, 0.0, w.y0[:100], w.params[:100], 0.5, rtol=1e-8, atol=1e-8)
+    done.run()
+    check(done)                                   # finished before the sink was set: delivered by the next launch
+    blow = ni.RK45(ni.rhs.blowup, 0.0, np.linspace(1.0, 2.0, 64)[:, None], 10.0, rtol=1e-8, atol=1e-8)
+    f = check(blow)
+    assert np.all(f['status'] != 1)               # y' = y^2 leaves every trajectory failed / non-finite before t = 10
+    # CTA-per-trajectory systems have no in-kernel sink
+    h = wl.c5_heat(N=2, n=100, t_bound=0.1)
+    big = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 0.1, rtol=1e-8, atol=1e-8)
+    with pytest.raises(ni.NiError):
+        big.set_terminal_sink([torch.zeros(1024, dtype=torch.uint8, device='cuda').data_ptr()])

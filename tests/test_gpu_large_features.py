@@ -89,16 +89,16 @@ def test_per_trajectory_step_limits_on_a_large_system():
 @pytest.mark.parametrize('n', [200, 333])
 def test_recording_on_cta_per_trajectory_kernels(n):
     """The record log of the large kernels (32 776 B per step at n = 4096): every accepted (t, y) of a fast-forward run
-    equals the lock-step sequence of a single solver bit for bit; the record slot is reserved one step ahead (the last
-    step of a trajectory reserves none, so no slot is wasted); a log that is too small stops the trajectories between
-    attempts, and draining + relaunching loses nothing."""
+    equals the lock-step sequence of a single solver bit for bit; a fast-forward run reserves its record slots eight at a
+    time per trajectory (the unused ones of the last chunk are tagged and skipped by the drain), lock-step calls one at a
+    time; a log that is too small stops the trajectories between attempts, and draining + relaunching loses nothing."""
     from numba_integrators_b200 import workloads as wl
     h = wl.c5_heat(N=24, n=n, t_bound=1.0)
     make = lambda **kw: ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 1.0, rtol=1e-8, atol=1e-8, **kw)
     ens = make(record=20_000)
     assert ens.run() == 0
     total = int(ens.n_accepted.sum())
-    assert ens.record_count() == total
+    assert total <= ens.record_count() <= total + 7 * ens.N    # slots in use, the tagged leftovers included
     rec = ens.record_drain().sorted()
     assert len(rec) == total
     for k in (0, 7, 23):

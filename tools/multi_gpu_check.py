@@ -2,8 +2,9 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multi_gpu_check.py
 
-Every rank integrates its shard (contiguous blocks for C3, interleaved for the sorted C4 sweep); the NCCL gather
-must give every rank the full result in global order, bit-identical to rank 0 integrating everything alone."""
+Every rank integrates its shard (contiguous blocks for C3, interleaved for the sorted C4 sweep); the NCCL gather, the
+peer-store gather and the gather fused into the run kernel must each give every rank the full result in global order,
+bit-identical to rank 0 integrating everything alone."""
 import os
 import sys
 from pathlib import Path
@@ -33,6 +34,22 @@ for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False)
     full = nd.gather(ens, N_global=w.N, interleaved=interleaved)
     full_p = nd.gather(ens, N_global=w.N, interleaved=interleaved, peer=True)  # fused pack + peer stores over NVLink
     same_p = all(np.array_equal(full[k], full_p[k]) for k in full)
+    # the gather fused into the integration: a fresh ensemble whose run kernel stores the terminal records to every
+    # GPU's receive buffer while it integrates (FusedGather); what follows the run is a barrier
+    if w.advanced:
+        ens2 = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, arrays['y0'], arrays['params'], w.t_bound, rtol=w.rtol, atol=w.atol)
+    else:
+        ens2 = ni.RK23(f(*arrays['params'].T), w.t0, arrays['y0'], w.t_bound, rtol=w.rtol, atol=w.atol)
+    ens2.sync()
+    ens2.set_stream(torch.cuda.current_stream().cuda_stream)
+    fg = nd.FusedGather(ens2, w.N, interleaved)
+    fg.begin()
+    ens2.run_async()
+    fg.finish()
+    torch.cuda.synchronize()
+    full_f = fg.host()
+    same_p = same_p and all(np.array_equal(full[k], full_f[k]) for k in full)
+    fused_impl = fg.impl
     if rank == 0:
         if w.advanced:
             ref = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, w.y0, w.params, w.t_bound, rtol=w.rtol, atol=w.atol)
@@ -46,7 +63,7 @@ for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False)
             same = same and np.array_equal(full['auxiliary'], ref.auxiliary)
         same = same and same_p
         print(f'{name}: world={world} N={w.N} shard sizes ~{len(idx)} interleaved={interleaved} '
-              f'gather (NCCL and peer-store) == single-GPU run: {same}; accepted {int(full["n_accepted"].sum())}')
+              f'gather (NCCL, peer-store and fused [{fused_impl}]) == single-GPU run: {same}; accepted {int(full["n_accepted"].sum())}')
         ok = ok and same
 flag = torch.tensor([1 if ok else 0], device='cuda')
 dist.broadcast(flag, 0)
