@@ -225,6 +225,12 @@ int ni_ensemble_pack_terminal_peers(ni_ensemble *e, void *const *dst_device, int
  * the one collective of the path (reference: none -- single process) then costs a barrier after the run,
  * not a transfer.  n_dst = 0 switches the sink off.  The setting is part of the launch arguments of every later run. */
 int ni_ensemble_terminal_sink_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory);
+/* Stiffness probe (the reference has none): rho_host[i] = estimate of the spectral radius of df/dy at
+ * trajectory i's current (t, y), by `iterations` steps of the nonlinear power iteration v <- f(y + eps v) - f(y) started
+ * from v = f(y) (a mode of the init kernel: works for every right-hand side, nothing is modified).  h_abs * rho near the
+ * method's real stability interval (RK45 ~3.3, RK23 ~2.5) means the step size is limited by stability, not accuracy:
+ * the problem is stiff at this tolerance and an explicit pair is the wrong tool.  Synchronous. */
+int ni_ensemble_stiffness(ni_ensemble *e, int iterations, double *rho_host);
 int ni_ensemble_set_terminal_sink(ni_ensemble *e, void *const *dst_device, int n_dst, int64_t first_row);
 
 

@@ -444,6 +444,24 @@ class Ensemble:
         arr = (_lib._vp * len(dst_device_ptrs))(*[int(p) for p in dst_device_ptrs])
         check(self._L.ni_ensemble_pack_terminal_peers(self._h, arr, len(dst_device_ptrs)))
 
+    # real stability interval of the two pairs (|R(z)| <= 1 for z in [-limit, 0]): Bogacki-Shampine 3(2), Dormand-Prince 5(4)
+    STABILITY_LIMIT = {_lib.RK23: 2.51, _lib.RK45: 3.31}
+
+    def stiffness(self, iterations=12):
+        """Stiffness probe (the reference has none).  For every trajectory: `rho`, an estimate of the
+        spectral radius of df/dy at its current (t, y) (nonlinear power iteration on the device, any right-hand side),
+        `h_rho = h_abs * rho`, and `stiff = h_rho > 0.5 * limit` with `limit` the real stability interval of the method
+        (RK45 3.31, RK23 2.51): the controller's step size sits at the stability boundary instead of being chosen by
+        the tolerance -- Hairer & Wanner's test in DOPRI5 -- so an explicit pair pays in rejected steps (C5: 0.6 per
+        accepted step).  Nothing is modified.  Ask between steps of a run (`ni.step`, `ff2cond`): the step that is clipped
+        to `t_bound` / to the end of an `ff2t` leg leaves a small `h_abs` behind (_basic.py:153-156)."""
+        rho = np.empty(self.N)
+        check(self._L.ni_ensemble_stiffness(self._h, int(iterations), rho.ctypes.data))
+        limit = self.STABILITY_LIMIT[self._method]
+        h_rho = np.atleast_1d(self.h_abs) * rho
+        out = {'rho': rho, 'h_rho': h_rho, 'limit': limit, 'stiff': h_rho > 0.5 * limit}
+        return {k: (v[0] if self._single and isinstance(v, np.ndarray) else v) for k, v in out.items()}
+
     def terminal_sink_dtype(self):
         """numpy dtype of one row of an in-kernel terminal sink: the fields of terminal_dtype(), rows padded to a multiple
         of 16 bytes (ni_ensemble_terminal_sink_bytes: 64 for Lorenz-63)."""

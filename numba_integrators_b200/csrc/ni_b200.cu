@@ -1479,6 +1479,31 @@ NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_t
   return NI_OK;
 }
 
+// Stiffness probe: spectral-radius estimate of df/dy at every trajectory's current state.
+NI_API int ni_ensemble_stiffness(ni_ensemble *e, int iterations, double *rho_host) {
+  if (!e || !rho_host || iterations < 1 || iterations > 1000)
+    return fail(NI_ERR_INVALID, "need an ensemble, an output buffer and 1..1000 iterations");
+  if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
+  CU(cudaSetDevice(e->device));
+  if (int rc = need_scratch(e, (size_t)e->N * 8)) return rc;
+  e->a.probe_iters = iterations;
+  e->a.probe_out = (double *)e->scratch;
+  int grid;
+  if (e->mod.kind == NI_KIND_LARGE) {
+    grid = run_grid(e);
+  } else {
+    long long need = (e->N + NI_BLOCK - 1) / NI_BLOCK, cap = (long long)e->sms * 16;
+    grid = (int)(need < cap ? need : cap);
+  }
+  const int rc = launch(e, e->mod.k_init, grid, e->mod.block, e->mod.kind == NI_KIND_LARGE ? e->mod.smem : 0);
+  e->a.probe_iters = 0;  // the init kernel initialises again
+  e->a.probe_out = nullptr;
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(rho_host, e->scratch, (size_t)e->N * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
 NI_API int ni_ensemble_terminal_sink_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory) {
   if (!e || !bytes_per_trajectory) return fail(NI_ERR_INVALID, "ensemble / bytes_per_trajectory is NULL");
   *bytes_per_trajectory = 16 * (int64_t)ni_sink_vectors(e->mod.n, e->mod.Q);

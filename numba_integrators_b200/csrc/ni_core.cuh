@@ -116,6 +116,10 @@ struct NiArgs {
   unsigned int *sink[NI_SINK_MAX];
   int sink_n;                   // 0: no sink
   long long sink_row0;
+  // stiffness probe: with probe_iters > 0 the INIT kernel does not initialise anything; it estimates the
+  // spectral radius of df/dy at every trajectory's current (t, y) by a nonlinear power iteration and writes it to probe_out
+  int probe_iters;
+  double *probe_out;            // [N]
   // ff2cond: built-in predicate parameters
   int cond_kind;                // 0: no predicate; != 0: ff2cond launch of a kernel compiled with a predicate
   int cond_index;
@@ -524,10 +528,66 @@ __device__ __forceinline__ bool ni_user_cond(double t, const double *y, const do
 // RK.__init__ (_basic.py:203-242): FSAL seed K[-1] = f(t0, y0), direction, error exponent,
 // select_initial_step (_basic.py:33-89) unless first_step is given.  Also transposes the
 // row-major host layout into the component-major device layout.
+// Stiffness probe (a mode of the init kernel, so that every right-hand side -- built-in, NVRTC, Python-translated -- has
+// it without another kernel): rho ~ spectral radius of J = df/dy at the trajectory's current (t, y) by the nonlinear
+// power iteration of the stabilised-RK codes (v <- f(y + eps v) - f(y), rho_k = |v_new| / (eps |v|)), started from
+// v = f(y).  h_abs * rho against the method's real stability interval (RK45 3.3, RK23 2.5) tells whether the
+// controller's step is limited by stability rather than accuracy (Hairer / Wanner IV.2: the test DOPRI5 applies).
+template <class Rhs>
+NI_DEV void ni_small_probe_body(const NiArgs &a) {
+  constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
+  const long long N = a.N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < N;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double y[n], f0[n], v[n], y1[n], f1[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];
+#pragma unroll
+    for (int i = 0; i < n; ++i) y[i] = a.y[i * N + idx];
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = a.params[i * N + idx];
+    const double t = a.t[idx];
+    Rhs::template eval<false>(t, y, p, f0, aux);
+    double yn2 = 0.0, vn2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      v[i] = f0[i];
+      yn2 += y[i] * y[i];
+      vn2 += v[i] * v[i];
+    }
+    if (!(vn2 > 0.0)) {  // an equilibrium (or a non-finite right-hand side): probe along (1, ..., 1)
+#pragma unroll
+      for (int i = 0; i < n; ++i) v[i] = 1.0;
+      vn2 = (double)n;
+    }
+    const double ynorm = sqrt(yn2);
+    double rho = 0.0;
+    for (int it = 0; it < a.probe_iters; ++it) {
+      const double vnorm = sqrt(vn2);
+      const double eps = 1.4901161193847656e-08 * (1.0 + ynorm) / vnorm;  // sqrt(machine epsilon), relative to |y|
+#pragma unroll
+      for (int i = 0; i < n; ++i) y1[i] = y[i] + eps * v[i];
+      Rhs::template eval<false>(t, y1, p, f1, aux);
+      double dn2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        v[i] = f1[i] - f0[i];
+        dn2 += v[i] * v[i];
+      }
+      rho = sqrt(dn2) / (eps * vnorm);
+      if (!(dn2 > 0.0)) break;  // J v = 0 (or not finite): rho stays what the last iteration found
+      vn2 = dn2;
+    }
+    a.probe_out[idx] = rho;
+  }
+}
+
 template <class Rhs, int METHOD>
 NI_DEV void ni_small_init_body(const NiArgs &a) {
   constexpr int n = Rhs::N, P = Rhs::P, Q = Rhs::Q;
   const long long N = a.N;
+  if (a.probe_iters > 0) {
+    ni_small_probe_body<Rhs>(a);
+    return;
+  }
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < N;
        idx += (long long)gridDim.x * blockDim.x) {
     double y[n], f0[n], p[P > 0 ? P : 1], aux[Q > 0 ? Q : 1];

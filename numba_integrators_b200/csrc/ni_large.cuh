@@ -250,11 +250,72 @@ NI_DEV void ni_large_store_aux(const NiArgs &a, NiLargeCtx &c, long long idx, do
 }
 
 // ---------------------------------------------------------------- init (RK.__init__ + select_initial_step)
+// Stiffness probe of the CTA-per-trajectory systems (see ni_small_probe_body): the same power iteration with the
+// norms taken across the CTA.
+template <class Rhs, int CPT>
+NI_DEV void ni_large_probe_body(const NiArgs &a, NiLargeCtx &c) {
+  constexpr int P = Rhs::P;
+  const int n = c.n;
+  for (long long idx = blockIdx.x; idx < a.N; idx += gridDim.x) {
+    double y[CPT], f0[CPT], v[CPT], y1[CPT], f1[CPT], p[P > 0 ? P : 1];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int j = ni_large_j<Rhs>(c, i);
+      y[i] = j < n ? a.y[idx * n + j] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = a.params[idx * P + i];
+    const double t = a.t[idx];
+    int parity = 0;
+    ni_large_rhs<Rhs, CPT, false>(c, t, y, p, parity, f0);
+    parity ^= 1;
+    double ys = 0.0, vs = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      v[i] = ni_large_j<Rhs>(c, i) < n ? f0[i] : 0.0;
+      ys += y[i] * y[i];
+      vs += v[i] * v[i];
+    }
+    const double ynorm = sqrt(ni_large_block_sum(c, ys, 0));
+    double vn2 = ni_large_block_sum(c, vs, 1);
+    if (!(vn2 > 0.0)) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) v[i] = ni_large_j<Rhs>(c, i) < n ? 1.0 : 0.0;
+      vn2 = (double)n;
+    }
+    double rho = 0.0;
+    for (int it = 0; it < a.probe_iters; ++it) {
+      const double vnorm = sqrt(vn2);
+      const double eps = 1.4901161193847656e-08 * (1.0 + ynorm) / vnorm;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) y1[i] = y[i] + eps * v[i];
+      ni_large_rhs<Rhs, CPT, false>(c, t, y1, p, parity, f1);
+      parity ^= 1;
+      double ds = 0.0;
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        v[i] = ni_large_j<Rhs>(c, i) < n ? f1[i] - f0[i] : 0.0;
+        ds += v[i] * v[i];
+      }
+      const double dn2 = ni_large_block_sum(c, ds, it & 1);
+      rho = sqrt(dn2) / (eps * vnorm);
+      if (!(dn2 > 0.0)) break;  // (uniform across the CTA)
+      vn2 = dn2;
+    }
+    if (c.tid == 0) a.probe_out[idx] = rho;
+    __syncthreads();
+  }
+}
+
 template <class Rhs, int METHOD, int CPT>
 NI_DEV void ni_large_init_body(const NiArgs &a, double *smem) {
   constexpr int P = Rhs::P;
   NiLargeCtx c = ni_large_ctx(a, smem, CPT, NiLargeSlots<METHOD>::TOTAL);
   const int n = c.n;
+  if (a.probe_iters > 0) {
+    ni_large_probe_body<Rhs, CPT>(a, c);
+    return;
+  }
   for (long long idx = blockIdx.x; idx < a.N; idx += gridDim.x) {
     double y[CPT], f0[CPT], p[P > 0 ? P : 1], rt[CPT], at[CPT];
 #pragma unroll

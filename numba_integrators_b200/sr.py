@@ -1,6 +1,12 @@
 """`ni.sr`: the reference's StructRef flavour of RK45 (`_structref.py:19-144`): the same algorithm with the
 state fields named `x` / `x_bound` and a free `step(state)` function.  Like `step_advanced` (and unlike the basic
-jitclass solver) it applies `direction` to the step (`_structref.py:37`), so backward integration works."""
+jitclass solver) it applies `direction` to the step (`_structref.py:37`), so backward integration works.
+
+One documented deviation: the kernels behind this facade are the `step_advanced` ones, whose terminal `step()` call (the
+one that finds `t == t_bound`) overwrites `step_size` with the proposed next step (`_advanced.py:151`); the reference's
+StructRef `step` returns False there without touching the state (`_structref.py:21-22`).  After
+`while sr.step(s): pass` every other field equals the reference's; `s.step_size` is the unsigned proposal, not the last
+signed step."""
 from __future__ import annotations
 
 import numpy as np

@@ -645,3 +645,44 @@ def test_terminal_sink_written_by_the_run_kernel():
     big = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 0.1, rtol=1e-8, atol=1e-8)
     with pytest.raises(ni.NiError):
         big.set_terminal_sink([torch.zeros(1024, dtype=torch.uint8, device='cuda').data_ptr()])
+
+
+def test_stiffness_probe():
+    """ni_ensemble_stiffness: spectral-radius estimate of df/dy at the current state, for every kind of
+    right-hand side; h_abs * rho against the method's stability interval separates the stability-limited heat equation
+    from accuracy-limited problems."""
+    from numba_integrators_b200 import workloads as wl
+    # harmonic oscillator: J = [[0, 1], [-1, 0]] has |J v| = |v| for every v
+    rng = np.random.default_rng(5)
+    ho = ni.RK45(ni.rhs.harmonic, 0.0, rng.uniform(-1, 1, size=(100, 2)), 10.0, rtol=1e-8, atol=1e-8)
+    ho.run()
+    s = ho.stiffness()
+    assert np.allclose(s['rho'], 1.0, rtol=1e-6) and not s['stiff'].any()
+    # a Python right-hand side (translated), linear with eigenvalues -1 and -1000
+    def f(t, y):
+        return np.array((-y[0], -1000.0 * y[1]))
+    lin = ni.RK45(f, 0.0, np.array((1.0, 1.0)), 5.0, rtol=1e-6, atol=1e-9)
+    for _ in range(300):          # (mid-run: the clip of the last step to t_bound would leave a small h_abs behind)
+        assert ni.step(lin)
+    r = lin.stiffness()
+    assert abs(r['rho'] - 1000.0) < 1.0 and r['stiff'] and 1.5 < r['h_rho'] < 12.0   # the proposed step hovers around the stability limit (3.3)
+    # Lorenz at tol 1e-8: accuracy-limited
+    w = wl.c3_lorenz(N=500, t_bound=2.0)
+    lo = ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 2.0, rtol=1e-8, atol=1e-8)
+    lo.run()
+    sl = lo.stiffness()
+    assert np.all(sl['rho'] > 1.0) and np.all(sl['rho'] < 200.0) and not sl['stiff'].any()
+    before = (lo.y.copy(), lo.h_abs.copy(), lo.n_accepted.copy())
+    lo.stiffness(3)
+    assert np.array_equal(lo.y, before[0]) and np.array_equal(lo.h_abs, before[1]) and np.array_equal(lo.n_accepted, before[2])
+    # CTA-per-trajectory: 1-D heat equation, rho -> 4 k cos^2(pi / (2 (n + 1))), stability-limited steps
+    for n in (200, 1000):
+        h = wl.c5_heat(N=6, n=n, t_bound=50.0)
+        he = ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 50.0, rtol=1e-8, atol=1e-8)
+        for _ in range(150):
+            assert ni.step(he)
+        sh = he.stiffness(40)
+        exact = 4.0 * h.params[:, 0] * np.cos(np.pi / (2 * (n + 1))) ** 2
+        assert np.all(sh['rho'] <= exact * 1.0001) and np.all(sh['rho'] >= 0.9 * exact), (sh['rho'], exact)
+        # (an instantaneous indicator: right after a rejection the proposed step is below the boundary)
+        assert sh['stiff'].mean() >= 0.5 and np.all(sh['h_rho'] > 0.5) and np.all(sh['h_rho'] < 12.0), sh['h_rho']
