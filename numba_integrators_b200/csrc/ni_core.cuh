@@ -57,6 +57,12 @@
 #define NI_LEAN 1  // 0: every launch takes the general run body (A/B experiments)
 #endif
 
+#ifndef NI_EXP_ABSMAX_FP
+#define NI_EXP_ABSMAX_FP 1
+#endif
+#ifndef NI_EXP_NACC
+#define NI_EXP_NACC 1
+#endif
 #define NI_SINK_MAX 8  // destinations of the in-kernel terminal sink (the GPUs of one box)
 #define NI_FLAG_REC_OVERFLOW 1ull
 #define NI_REC_INVALID 0xffffffffu  // rec_traj value of a reserved-but-unused record slot
@@ -488,7 +494,16 @@ NI_DEV void ni_rk_attempt(const NiArgs &a, double t, double tn, double h, const 
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       num[i] = __dmul_rn(ev[i], h);
+#if NI_EXP_ABSMAX_FP
+      // max(|y|, |y_new|) by ONE FP64 compare and a select of the raw operand (the multiply takes |.| for free): two
+      // port cycles + two selects, where the integer-pipe version needs two sign masks and a two-word compare first.
+      // The FP64 pipe has the slack (the kernel is bound by the register ports, section 3.2 of DESIGN.md).  A NaN in
+      // y_new makes the compare false and is selected, i.e. propagates like np.maximum.
+      const double big = LITE ? (fabs(y[i]) > fabs(yn[i]) ? y[i] : yn[i]) : ni_absmax(y[i], yn[i]);
+      const double den = __dadd_rn(a.atol[i], __dmul_rn(fabs(big), a.rtol[i]));
+#else
       const double den = __dadd_rn(a.atol[i], __dmul_rn(ni_absmax(y[i], yn[i]), a.rtol[i]));
+#endif
       if constexpr (LITE) {
         const int hb = __double2hiint(den);
         den_hi = hb > den_hi ? hb : den_hi;
@@ -1319,7 +1334,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
     // (both clamps stay in line: the first rejection after the ten-fold growth from a small initial step usually has
     // an error norm above 1845, i.e. MIN_FACTOR -- sending it to the cold block cost C3 3 %)
     double fac = (unsigned)__double2hiint(sp) >= 0x40240000u ? 10.0 : sp;
+#if NI_EXP_ABSMAX_FP
+    fac = fac < NI_MC(2, 0.2) ? 0.2 : fac;  // (one FP64 compare with ONE register source: cheaper than the two-word integer compare)
+#else
     fac = ni_lt_pos(fac, 0.2) ? 0.2 : fac;
+#endif
     double h_new = __dmul_rn(h_abs, fac);
     // Lanes that need the cold block commit there; the hot commit below runs on predicates that never leave the
     // predicate registers (a flag merged across the cold call is materialised as a byte: six more instructions).
@@ -1343,7 +1362,11 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
 #pragma unroll
         for (int i = 0; i < n; ++i) y[i] = yn[i];
       }
+#if NI_EXP_NACC
+      nacc += (c.flags & 1) - (int)((unsigned)(__double2hiint(en) - 0x3ff00000) >> 31);  // (undo the count below)
+#else
       nacc += c.flags & 1;
+#endif
       if (c.flags & 8) {
         status = c.status;
         step_h = h;  // step_size of the exit
@@ -1362,7 +1385,13 @@ NI_DEV void ni_small_run_lean(const NiArgs &a) {
       kl[i] = kn[i];  // also after a rejection: the stale FSAL stage
     }
     h_abs = h_new;
+#if NI_EXP_NACC
+    // error_norm < 1 as the sign bit of hi(en) - hi(1.0), added with one LEA.HI (a predicated increment costs three
+    // instructions once ptxas has turned it into a select); a lane that took the cold block corrected its count there
+    nacc += (int)((unsigned)(__double2hiint(en) - 0x3ff00000) >> 31);
+#else
     nacc += take ? 1 : 0;
+#endif
     ++iter;
     if constexpr (REC) {
       // one slot per accepting lane, handed out by ballot rank: consecutive lanes write consecutive slots

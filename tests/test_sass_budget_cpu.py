@@ -19,9 +19,9 @@ sys.path.insert(0, str(ROOT / 'tools'))
 
 # label -> ((D, I, R, port cycles) budget of the lean body, the same of the general body)
 BUDGET = {
-    'c3 lorenz63 RK45 Advanced': ((239, 108, 990, 555), (244, 168, 1085, 642)),
-    'c4 vanderpol RK23 basic': ((96, 86, 446, 265), (101, 142, 535, 348)),
-    'c1 harmonic RK45 basic': ((137, 94, 592, 350), (142, 150, 682, 432)),
+    'c3 lorenz63 RK45 Advanced': ((243, 90, 975, 538), (244, 168, 1085, 642)),
+    'c4 vanderpol RK23 basic': ((99, 74, 436, 256), (101, 142, 535, 348)),
+    'c1 harmonic RK45 basic': ((140, 82, 584, 340), (142, 150, 682, 432)),
 }
 
 
@@ -37,5 +37,9 @@ def test_hot_loop_instruction_budget(label):
     for k, (hist, d, i) in enumerate(loops):
         d_max, i_max, r_max, p_max = BUDGET[label][k]
         assert hist['STL'] + hist['LDL'] == 0, (label, 'local memory in the hot loop', dict(hist))
-        assert hist['DSETP'] == 0, (label, 'FP64-pipe compare in the hot loop', dict(hist))
+        # FP64-pipe compares: the lean body spends one per component on max(|y|, |y_new|) and one on the MIN_FACTOR clamp
+        # (cheaper in register-port cycles than the two-word integer compares, and the pipe has the slack); the
+        # general body has none
+        n_state = {'c3 lorenz63 RK45 Advanced': 3, 'c4 vanderpol RK23 basic': 2, 'c1 harmonic RK45 basic': 2}[label]
+        assert hist['DSETP'] <= (n_state + 1 if k == 0 else 0), (label, 'FP64-pipe compares in the hot loop', dict(hist))
         assert d <= d_max and i <= i_max and hist['_reads'] <= r_max and hist['_ports'] <= p_max, (label, k, d, i, dict(hist))
