@@ -440,12 +440,23 @@ def main():
         tms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(tms2, op=dist.ReduceOp.MAX)
+        # single-shot latency: ONE ensemble, nothing overlapped -- upload, init, run, packed download, synchronise
+        barrier()
+        t_ss = time.perf_counter()
+        e0.record(s_a)
+        launch(0)
+        collect(0)
+        e1.record(s_a)
+        torch.cuda.synchronize()
+        single_wall_ms = (time.perf_counter() - t_ss) * 1e3
+        single_ms = e0.elapsed_time(e1)
         for o in (out, out_b):
             rec = o.numpy().view(rec_dt)
             acc_e2e = int(rec['n_accepted'].astype(np.int64).sum())
             assert acc_e2e == acc_rank and np.all(rec['status'] == _lib.ST_FINISHED), (acc_e2e, acc_rank)
         e2e = {'value': acc_all * args.steps / (float(tms2.item()) * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                'd2h_bytes_per_step': d2h, 'ms_per_step': float(tms2.item()) / args.steps,
+               'single_shot_ms': single_ms, 'single_shot_wall_ms': single_wall_ms,
                'path': 'ni_ensemble_upload(pinned) -> ni_ensemble_reset -> ni_ensemble_run_async -> '
                        'ni_ensemble_get_terminal (packed t, y, aux, counters, status: one copy), two ensembles '
                        'double-buffered on two CUDA streams'}
