@@ -231,6 +231,11 @@ int ni_ensemble_terminal_sink_bytes(const ni_ensemble *e, int64_t *bytes_per_tra
  * method's real stability interval (RK45 ~3.3, RK23 ~2.5) means the step size is limited by stability, not accuracy:
  * the problem is stiff at this tolerance and an explicit pair is the wrong tool.  Synchronous. */
 int ni_ensemble_stiffness(ni_ensemble *e, int iterations, double *rho_host);
+/* Guard mode (memory-safety evidence where compute-sanitizer is not available): an ensemble created while the
+ * environment variable NI_B200_GUARD=1 is set keeps every device buffer between two 64 KiB guard zones filled with 0xA5.
+ * *n_buffers = guarded buffers (0 when the mode is off), *bad_bytes = guard bytes that no longer hold the fill value,
+ * i.e. out-of-bounds writes of any kernel since creation (0 expected).  Synchronises the ensemble's stream. */
+int ni_ensemble_guard_check(ni_ensemble *e, int64_t *n_buffers, int64_t *bad_bytes);
 int ni_ensemble_set_terminal_sink(ni_ensemble *e, void *const *dst_device, int n_dst, int64_t first_row);
 
 

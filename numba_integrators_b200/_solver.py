@@ -462,6 +462,14 @@ class Ensemble:
         out = {'rho': rho, 'h_rho': h_rho, 'limit': limit, 'stiff': h_rho > 0.5 * limit}
         return {k: (v[0] if self._single and isinstance(v, np.ndarray) else v) for k, v in out.items()}
 
+    def guard_check(self):
+        """(guarded buffers, overwritten guard bytes) of an ensemble created with NI_B200_GUARD=1 in the environment:
+        every device buffer then sits between two 64 KiB zones of 0xA5 and any out-of-bounds write of a kernel shows up
+        here (compute-sanitizer is not available on the GPU pool)."""
+        nb, bad = C.c_int64(0), C.c_int64(0)
+        check(self._L.ni_ensemble_guard_check(self._h, nb, bad))
+        return nb.value, bad.value
+
     def terminal_sink_dtype(self):
         """numpy dtype of one row of an in-kernel terminal sink: the fields of terminal_dtype(), rows padded to a multiple
         of 16 bytes (ni_ensemble_terminal_sink_bytes: 64 for Lorenz-63)."""

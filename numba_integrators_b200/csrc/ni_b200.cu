@@ -531,6 +531,11 @@ struct ni_ensemble {
   unsigned char *flag_d = nullptr;
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  // guard mode (environment NI_B200_GUARD=1 when the ensemble is created; compute-sanitizer is closed on the GPU pool):
+  // every device allocation of the ensemble sits between two 64 KiB guard zones filled with 0xA5;
+  // ni_ensemble_guard_check counts the guard bytes a kernel has overwritten
+  bool guard = false;
+  std::vector<std::pair<void *, size_t>> guarded;  // (user pointer, user bytes) of every live allocation
   bool uploaded = false, initialised = false;
   int64_t max_attempts = 1ll << 40;
   // tail compaction (thread-per-trajectory kernels, fast-forward launches of ensembles that fill the GPU): the run is
@@ -559,14 +564,46 @@ struct ni_ensemble {
   int64_t step_calls = 0;  // capture + instantiation cost ~1.5 ms: only worth it for loops longer than ~100 steps
 };
 
+#define NI_GUARD_BYTES ((size_t)65536)
+#define NI_GUARD_FILL 0xA5
+// cudaMalloc / cudaFree of the ensemble's device buffers; in guard mode with a guard zone on either side
+static int gmalloc(ni_ensemble *e, void **out, size_t bytes) {
+  void *q = nullptr;
+  const size_t user = (bytes + 255) / 256 * 256;  // (the trailing guard starts on a 256-byte boundary)
+  cudaError_t ce = cudaMalloc(&q, e->guard ? user + 2 * NI_GUARD_BYTES : bytes);
+  if (ce != cudaSuccess) return fail(ce == cudaErrorMemoryAllocation ? NI_ERR_NOMEM : NI_ERR_CUDA, "cudaMalloc(%zu bytes): %s",
+                                     bytes, cudaGetErrorString(ce));
+  if (e->guard) {
+    if (cudaMemset(q, NI_GUARD_FILL, NI_GUARD_BYTES) != cudaSuccess ||
+        cudaMemset((char *)q + NI_GUARD_BYTES + user, NI_GUARD_FILL, NI_GUARD_BYTES) != cudaSuccess) {
+      cudaFree(q);
+      return fail(NI_ERR_CUDA, "cudaMemset of the guard zones failed");
+    }
+    q = (char *)q + NI_GUARD_BYTES;
+    e->guarded.emplace_back(q, user);
+  }
+  *out = q;
+  return NI_OK;
+}
+static void gfree(ni_ensemble *e, void *q) {
+  if (!q) return;
+  if (e->guard) {
+    for (size_t k = 0; k < e->guarded.size(); ++k)
+      if (e->guarded[k].first == q) {
+        e->guarded.erase(e->guarded.begin() + (long)k);
+        break;
+      }
+    q = (char *)q - NI_GUARD_BYTES;
+  }
+  cudaFree(q);
+}
+
 template <class T>
 static int dalloc(ni_ensemble *e, T **p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
   void *q = nullptr;
-  cudaError_t ce = cudaMalloc(&q, count * sizeof(T));
-  if (ce != cudaSuccess) return fail(ce == cudaErrorMemoryAllocation ? NI_ERR_NOMEM : NI_ERR_CUDA, "cudaMalloc(%zu bytes): %s",
-                                     count * sizeof(T), cudaGetErrorString(ce));
+  if (int rc = gmalloc(e, &q, count * sizeof(T))) return rc;
   e->allocs.push_back(q);
   *p = (T *)q;
   return NI_OK;
@@ -575,11 +612,10 @@ static int dalloc(ni_ensemble *e, T **p, size_t count) {
 static int need_scratch(ni_ensemble *e, size_t bytes) {
   if (bytes <= e->scratch_bytes) return NI_OK;
   void *q = nullptr;
-  cudaError_t ce = cudaMalloc(&q, bytes);
-  if (ce != cudaSuccess) return fail(NI_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(ce));
+  if (int rc = gmalloc(e, &q, bytes)) return rc;
   if (e->scratch) {
     cudaStreamSynchronize(e->stream);
-    cudaFree(e->scratch);
+    gfree(e, e->scratch);
   }
   e->scratch = q;
   e->scratch_bytes = bytes;
@@ -590,8 +626,8 @@ NI_API int ni_ensemble_destroy(ni_ensemble *e) {
   if (!e) return NI_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  for (void *p : e->allocs) cudaFree(p);
-  if (e->scratch) cudaFree(e->scratch);
+  for (void *p : e->allocs) gfree(e, p);
+  if (e->scratch) gfree(e, e->scratch);
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   g_pinned.put(e->q_host);
   for (auto &ev : e->ev)
@@ -612,6 +648,7 @@ NI_API int ni_ensemble_create(const ni_module *m, int device, int64_t N, ni_ense
   if (device < 0 || device >= ndev) return fail(NI_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
   CU(cudaSetDevice(device));
   ni_ensemble *e = new ni_ensemble;
+  if (const char *g = getenv("NI_B200_GUARD")) e->guard = atoi(g) != 0;
   e->mod = *m;
   e->mod.lib = nullptr;  // not owned
   e->device = device;
@@ -1479,6 +1516,25 @@ NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_t
   return NI_OK;
 }
 
+// Guard mode: how many guard bytes around the ensemble's device buffers have been overwritten (0 expected).
+NI_API int ni_ensemble_guard_check(ni_ensemble *e, int64_t *n_buffers, int64_t *bad_bytes) {
+  if (!e || !n_buffers || !bad_bytes) return fail(NI_ERR_INVALID, "ensemble / outputs are NULL");
+  *n_buffers = (int64_t)e->guarded.size();
+  *bad_bytes = 0;
+  if (!e->guard) return NI_OK;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  std::vector<unsigned char> h(NI_GUARD_BYTES);
+  for (const auto &g : e->guarded) {
+    const char *zones[2] = {(const char *)g.first - NI_GUARD_BYTES, (const char *)g.first + g.second};
+    for (const char *z : zones) {
+      CU(cudaMemcpy(h.data(), z, NI_GUARD_BYTES, cudaMemcpyDeviceToHost));
+      for (unsigned char c : h) *bad_bytes += c != NI_GUARD_FILL;
+    }
+  }
+  return NI_OK;
+}
+
 // Stiffness probe: spectral-radius estimate of df/dy at every trajectory's current state.
 NI_API int ni_ensemble_stiffness(ni_ensemble *e, int iterations, double *rho_host) {
   if (!e || !rho_host || iterations < 1 || iterations > 1000)
@@ -1594,7 +1650,7 @@ NI_API int ni_ensemble_record_enable(ni_ensemble *e, int64_t capacity) {
             e->allocs.erase(e->allocs.begin() + (long)k);
             break;
           }
-        cudaFree(q);
+        gfree(e, q);
       }
       a.rec_traj = nullptr;
       a.rec_t = a.rec_y = a.rec_aux = nullptr;
