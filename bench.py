@@ -287,6 +287,22 @@ def main():
     clocks = sampler.stop()
     launches = ens.timing()['launches'] - launches0 - 2 * args.warmup
     ms_max = reduce_max(ms)
+
+    def timed_ordered(e, acc_total):
+        """The same steps with the work queue in longest-first order, the cost being the attempts of the run just
+        timed (ni_ensemble_set_order): what a repeated sweep / an integration in legs can do against the tail."""
+        e.order_by_cost()
+        o_ms, o_run, o_acc, _ = timed_steps(e, 3, 1)
+        e.set_order(None)
+        o_ms_max = reduce_max(o_ms) / 3
+        return {'ms_per_step': o_ms_max, 'run_kernel_ms_max_over_ranks': reduce_max(o_run),
+                'value': acc_total / (o_ms_max * 1e-3),
+                'note': 'launch order = decreasing attempts of the previous run of the same ensemble (longest first); '
+                        'not part of `value`'}
+
+    ordered = None
+    if not record:
+        ordered = timed_ordered(ens, reduce_sum(acc_rank)[0])
     acc_all, = reduce_sum(acc_rank)
     value = acc_all * args.steps / (ms_max * 1e-3)
 
@@ -384,6 +400,9 @@ def main():
                   'note': 'the same trajectories a 1-GPU run integrates, sharded by index; efficiency = strong rate / '
                           '(weak whole-job rate, i.e. n_gpus x the per-GPU rate at full occupancy)'}
         strong['_fp64_flops'] = ws.flops_per_attempt * s_att_all  # -> frac below, once the peak is known
+        s_ordered = timed_ordered(ens_s, s_acc_all)
+        s_ordered['efficiency_vs_weak_per_gpu_rate'] = s_ordered['value'] / value
+        strong['cost_ordered'] = s_ordered
         s_fused = timed_fused(ens_s, args.traj, inter, s_acc_all)
         if s_fused is not None:
             s_fused['efficiency_vs_weak_incl_gather'] = s_fused['value_incl_gather'] / value
@@ -531,6 +550,8 @@ def main():
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline}
         if fast is not None:
             roofline['fast'] = fast
+        if ordered is not None:
+            line['cost_ordered'] = ordered
         if gather_ms is not None:
             # the one collective of the path, once per job after the last step: pack kernel + ONE NCCL
             # all_gather_into_tensor of equal-sized record slots (not part of `value`, which is the driver's weak-scaling

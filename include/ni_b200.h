@@ -231,6 +231,13 @@ int ni_ensemble_terminal_sink_bytes(const ni_ensemble *e, int64_t *bytes_per_tra
  * method's real stability interval (RK45 ~3.3, RK23 ~2.5) means the step size is limited by stability, not accuracy:
  * the problem is stiff at this tolerance and an explicit pair is the wrong tool.  Synchronous. */
 int ni_ensemble_stiffness(ni_ensemble *e, int iterations, double *rho_host);
+/* Launch order of the run kernels' work queue: the persistent grid pops order[0], order[1], ... instead of 0, 1, ...
+ * (order = a permutation of 0..N-1 in host memory, copied; NULL restores the identity).  Results do not depend on it
+ * -- a trajectory's arithmetic never depends on what shares its warp -- but the END of a run does: the last
+ * trajectories popped finish alone, so the run ends one trajectory-duration after the queue is empty.  Handing out the
+ * expensive trajectories first (longest-processing-time-first, e.g. by the step counts of the previous run or leg of the
+ * same ensemble, or by a known cost parameter such as mu of a Van der Pol sweep) leaves the cheap ones for the tail. */
+int ni_ensemble_set_order(ni_ensemble *e, const uint32_t *order_host);
 /* Guard mode (memory-safety evidence where compute-sanitizer is not available): an ensemble created while the
  * environment variable NI_B200_GUARD=1 is set keeps every device buffer between two 64 KiB guard zones filled with 0xA5.
  * *n_buffers = guarded buffers (0 when the mode is off), *bad_bytes = guard bytes that no longer hold the fill value,

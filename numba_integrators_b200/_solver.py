@@ -462,6 +462,28 @@ class Ensemble:
         out = {'rho': rho, 'h_rho': h_rho, 'limit': limit, 'stiff': h_rho > 0.5 * limit}
         return {k: (v[0] if self._single and isinstance(v, np.ndarray) else v) for k, v in out.items()}
 
+    def set_order(self, order=None):
+        """Launch order of the work queue: `order` is a permutation of range(N) (the persistent kernel pops order[0],
+        order[1], ...), None restores 0, 1, 2, ...  Results are independent of it; the tail of a run is not: hand out the
+        expensive trajectories first (see `order_by_cost`)."""
+        if order is None:
+            check(self._L.ni_ensemble_set_order(self._h, None))
+            return
+        o = np.ascontiguousarray(order, dtype=np.uint32)
+        if o.shape != (self.N,):
+            raise ValueError(f'order must have {self.N} entries')
+        check(self._L.ni_ensemble_set_order(self._h, o.ctypes.data))
+
+    def order_by_cost(self, cost=None):
+        """Longest-processing-time-first launch order: trajectories sorted by decreasing `cost` (default: the attempts
+        n_accepted + n_rejected they took so far -- the previous run or leg of the same ensemble, the natural predictor
+        for repeated sweeps and for integration in legs).  Returns the order that was set."""
+        if cost is None:
+            cost = np.atleast_1d(self.n_accepted).astype(np.int64) + np.atleast_1d(self.n_rejected)
+        order = np.argsort(-np.asarray(cost), kind='stable').astype(np.uint32)
+        self.set_order(order)
+        return order
+
     def guard_check(self):
         """(guarded buffers, overwritten guard bytes) of an ensemble created with NI_B200_GUARD=1 in the environment:
         every device buffer then sits between two 64 KiB zones of 0xA5 and any out-of-bounds write of a kernel shows up

@@ -534,6 +534,10 @@ struct ni_ensemble {
   // guard mode (environment NI_B200_GUARD=1 when the ensemble is created; compute-sanitizer is closed on the GPU pool):
   // every device allocation of the ensemble sits between two 64 KiB guard zones filled with 0xA5;
   // ni_ensemble_guard_check counts the guard bytes a kernel has overwritten
+  // launch order (ni_ensemble_set_order): the work queue of a run hands out order_d[0], order_d[1], ... instead of
+  // 0, 1, ...; NULL = identity
+  unsigned int *order_d = nullptr;
+  unsigned long long *order_n_d = nullptr;
   bool guard = false;
   std::vector<std::pair<void *, size_t>> guarded;  // (user pointer, user bytes) of every live allocation
   bool uploaded = false, initialised = false;
@@ -933,8 +937,8 @@ static int launch_run(ni_ensemble *e, int64_t max_accepts, bool timed) {
   int rc = NI_OK;
   for (int k = 0; k < passes && rc == NI_OK; ++k) {
     e->a.queue = e->queue_all + 8 * k;
-    e->a.work_list = k == 0 ? nullptr : e->park_list[(k - 1) & 1];
-    e->a.work_count = k == 0 ? nullptr : e->queue_all + 8 * (k - 1) + 4;
+    e->a.work_list = k == 0 ? e->order_d : e->park_list[(k - 1) & 1];
+    e->a.work_count = k == 0 ? e->order_n_d : e->queue_all + 8 * (k - 1) + 4;
     e->a.park_list = e->park_list[k & 1];
     e->a.park_below = k + 1 < passes ? e->park_below : 0;  // the last pass finishes everything it holds
     rc = launch(e, e->mod.k_run[rec ? 1 : 0], run_grid(e), e->mod.block, e->mod.smem);
@@ -1513,6 +1517,45 @@ NI_API int ni_ensemble_set(ni_ensemble *e, int field, const void *host_in) {
 NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_trajectory) {
   if (!e || !bytes_per_trajectory) return fail(NI_ERR_INVALID, "ensemble / bytes_per_trajectory is NULL");
   *bytes_per_trajectory = 8ll * (1 + e->mod.n + e->mod.Q) + 12;
+  return NI_OK;
+}
+
+// Launch order of the work queue (longest-processing-time-first scheduling against the tail of a run).
+NI_API int ni_ensemble_set_order(ni_ensemble *e, const uint32_t *order_host) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  CU(cudaSetDevice(e->device));
+  if (!order_host) {  // back to 0, 1, 2, ...
+    CU(cudaStreamSynchronize(e->stream));
+    auto drop = [&](void *q) {
+      if (!q) return;
+      for (size_t k = 0; k < e->allocs.size(); ++k)
+        if (e->allocs[k] == q) {
+          e->allocs.erase(e->allocs.begin() + (long)k);
+          break;
+        }
+      gfree(e, q);
+    };
+    drop(e->order_d);
+    drop(e->order_n_d);
+    e->order_d = nullptr;
+    e->order_n_d = nullptr;
+    return NI_OK;
+  }
+  const size_t N = (size_t)e->N;
+  std::vector<bool> seen(N, false);
+  for (size_t i = 0; i < N; ++i) {
+    const uint32_t v = order_host[i];
+    if (v >= N || seen[v]) return fail(NI_ERR_INVALID, "order is not a permutation of 0..N-1 (entry %zu = %u)", i, v);
+    seen[v] = true;
+  }
+  if (!e->order_d) {
+    if (int rc = dalloc(e, &e->order_d, N)) return rc;
+    if (int rc = dalloc(e, &e->order_n_d, 1)) return rc;
+  }
+  const unsigned long long n64 = (unsigned long long)N;
+  CU(cudaMemcpyAsync(e->order_d, order_host, N * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->order_n_d, &n64, sizeof(n64), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));  // (order_host and n64 are the caller's / this frame's)
   return NI_OK;
 }
 

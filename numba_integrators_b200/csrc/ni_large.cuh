@@ -416,6 +416,7 @@ NI_DEV void ni_large_run_body(const NiArgs &a, double *smem) {
     // ---- next trajectory (one queue pop per CTA)
     if (tid == 0) {
       long long idx = (long long)atomicAdd(a.queue, 1ull);
+      if (a.work_list) idx = idx < (long long)*a.work_count ? (long long)a.work_list[idx] : a.N;  // ni_ensemble_set_order
       if (REC && (((volatile unsigned long long *)a.queue)[1] & NI_FLAG_REC_OVERFLOW)) idx = a.N;
       c.bcast[0] = idx;
       if (REC) c.bcast[3] = c.bcast[4] = c.bcast[5] = 0;  // this trajectory holds no record slots yet

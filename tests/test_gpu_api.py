@@ -686,3 +686,44 @@ def test_stiffness_probe():
         assert np.all(sh['rho'] <= exact * 1.0001) and np.all(sh['rho'] >= 0.9 * exact), (sh['rho'], exact)
         # (an instantaneous indicator: right after a rejection the proposed step is below the boundary)
         assert sh['stiff'].mean() >= 0.5 and np.all(sh['h_rho'] > 0.5) and np.all(sh['h_rho'] < 12.0), sh['h_rho']
+
+
+def test_launch_order_changes_nothing_but_the_schedule():
+    """ni_ensemble_set_order: the work queue hands the trajectories out in a caller-given order (longest first against
+    the tail of a run); every result stays bit-identical -- both layouts, recording included."""
+    from numba_integrators_b200 import workloads as wl
+    w = wl.c3_lorenz(N=5003, t_bound=1.0)
+    make = lambda: ni.Advanced(3, 1, ni.RK45)(ni.rhs.lorenz63, 0.0, w.y0, w.params, 1.0, rtol=1e-8, atol=1e-8)
+    ref = make()
+    ref.run()
+    rng = np.random.default_rng(9)
+    a = make()
+    a.set_order(rng.permutation(w.N))
+    a.run()
+    b = make()
+    order = b.order_by_cost(ref.n_accepted + ref.n_rejected)
+    assert np.array_equal(np.sort(order), np.arange(w.N)) and (ref.n_accepted + ref.n_rejected)[order[0]] == (ref.n_accepted + ref.n_rejected).max()
+    b.run()
+    assert np.array_equal(b.y, ref.y)
+    b.set_order(None)
+    own = b.order_by_cost()    # default cost: the attempts of the ensemble's own previous run
+    assert np.array_equal(own, order)
+    b.reset()
+    b.run()
+    for e in (a, b):
+        assert np.array_equal(e.y, ref.y) and np.array_equal(e.t, ref.t) and np.array_equal(e.auxiliary, ref.auxiliary)
+        assert np.array_equal(e.n_accepted, ref.n_accepted) and np.array_equal(e.n_rejected, ref.n_rejected)
+    with pytest.raises(ni.NiError):
+        a.set_order(np.zeros(w.N, dtype=np.uint32))        # not a permutation
+    with pytest.raises(ValueError):
+        a.set_order(np.arange(10))
+    # CTA-per-trajectory layout, with recording
+    h = wl.c5_heat(N=9, n=300, t_bound=1.0)
+    mk = lambda: ni.RK45(ni.rhs.heat1d(h.params[:, 0]), 0.0, h.y0, 1.0, rtol=1e-8, atol=1e-8, record=4000)
+    c, d = mk(), mk()
+    c.run()
+    d.set_order(np.arange(9)[::-1].copy())
+    d.run()
+    assert np.array_equal(c.y, d.y) and np.array_equal(c.n_accepted, d.n_accepted)
+    rc, rd = c.record_drain().sorted(), d.record_drain().sorted()
+    assert np.array_equal(rc.t, rd.t) and np.array_equal(rc.y, rd.y) and np.array_equal(rc.traj, rd.traj)
