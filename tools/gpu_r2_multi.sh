@@ -11,4 +11,5 @@ import json,sys
 d=json.loads(sys.stdin.read())
 print('value %.4g  ms %.2f  gather %.3f ms  incl %.4g  GB/s/rank %.0f'%(d['value'], d['ms_per_step'], d['final_gather_ms'], d['value_incl_gather'], d['gather_GBps_per_rank']))
 s=d['strong']; print('strong:', {k:(round(v,4) if isinstance(v,float) else v) for k,v in s.items() if k!='note'})
-print('e2e %.4g frac %.4f fast %.4f'%(d['e2e']['value'], d['roofline']['frac'], d['roofline']['fast']['frac']))"
+print('e2e %.4g frac %.4f fast %.4f'%(d['e2e']['value'], d['roofline']['frac'], d['roofline']['fast']['frac']))
+print('fused', d.get('fused_gather')); print('ordered', d.get('cost_ordered'))"
