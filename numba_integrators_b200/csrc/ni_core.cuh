@@ -57,6 +57,8 @@
 #define NI_LEAN 1  // 0: every launch takes the general run body (A/B experiments)
 #endif
 
+// A/B switches of the round-2 register-port work (profiles/r02_port_model.txt): all on in the
+// product; `tools/variant.sh <tag> -DNI_EXP_...=0` builds a library without one of them for tools/exp_c3.sh.
 #ifndef NI_EXP_ABSMAX_FP
 #define NI_EXP_ABSMAX_FP 1
 #endif
