@@ -98,3 +98,27 @@ def test_gather_world_size_2_gloo(interleaved):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_merge_of_padded_sink_records():
+    """Rows of the in-kernel terminal sink (ni_ensemble_set_terminal_sink / FusedGather) are the packed record padded to
+    16-byte vectors: the host-side merge must read them through the padded dtype and ignore the padding."""
+    from numba_integrators_b200._solver import terminal_dtype
+    n, Q, N, world = 3, 1, 11, 3
+    dt = terminal_dtype(n, Q)
+    assert dt.itemsize == 52
+    padded = np.dtype({'names': list(dt.names), 'formats': [dt.fields[k][0] for k in dt.names],
+                       'offsets': [dt.fields[k][1] for k in dt.names], 'itemsize': 64})
+    full = _records(N, n, Q)
+    rows = nd.shard_rows(N, world)
+    for inter in (False, True):
+        raw = np.full((world, rows * 64), 0xEE, dtype=np.uint8)       # padding bytes hold garbage
+        for r in range(world):
+            idx = nd.shard_indices(N, r, world, inter)
+            view = raw[r].view(padded)
+            for name in dt.names:
+                view[name][:len(idx)] = full[name][idx]
+        out = nd.merge_records(raw.view(padded).reshape(world, rows), N, world, inter)
+        assert np.array_equal(out['y'], full['y']) and np.array_equal(out['t'], full['t'])
+        assert np.array_equal(out['auxiliary'], full['aux']) and np.array_equal(out['n_accepted'], full['n_accepted'])
+        assert np.array_equal(out['status'], full['status'])
