@@ -154,8 +154,7 @@ class PeerGather(TerminalGather):
             self.recv = torch.zeros((self.world, nbytes), dtype=torch.uint8, device=dev)
         self.send = self.recv[self.rank]
 
-    @staticmethod
-    def _record_dtype(ens):
+    def _record_dtype(self, ens):
         return ens.terminal_dtype()
 
     @property
@@ -182,15 +181,20 @@ class FusedGather(PeerGather):
     the NCCL collective."""
 
     def __init__(self, ens, N_global, interleaved=False, group=None):
+        # CTA-per-trajectory systems have no in-kernel sink (their run kernel sits at the register limit; a 32 KB row per
+        # trajectory is also not worth hiding): `finish` packs and stores to the peers after the run, like PeerGather
+        self.in_kernel = ens.kind == 0
         PeerGather.__init__(self, ens, N_global, interleaved, group)
-        ens.set_terminal_sink(self.dst if self.hdl is not None else [self.send.data_ptr()], 0)
+        if self.in_kernel:
+            ens.set_terminal_sink(self.dst if self.hdl is not None else [self.send.data_ptr()], 0)
 
-    @staticmethod
-    def _record_dtype(ens):
-        return ens.terminal_sink_dtype()
+    def _record_dtype(self, ens):
+        return ens.terminal_sink_dtype() if ens.kind == 0 else ens.terminal_dtype()
 
     @property
     def impl(self):
+        if not self.in_kernel:
+            return PeerGather.impl.fget(self) + ' (CTA-per-trajectory kernels: after the run)'
         return 'peer stores over NVLink from the run kernel\'s retire path (symmetric memory): gather fused into the ' \
                'integration' if self.hdl is not None else 'run kernel writes the local slot, NCCL all_gather_into_tensor'
 
@@ -202,6 +206,11 @@ class FusedGather(PeerGather):
     def finish(self):
         """After the run (same stream): every rank's records have landed."""
         import torch.distributed as dist
+        if not self.in_kernel:
+            if self.hdl is not None:
+                self.ens.pack_terminal_peers(self.dst)
+            else:
+                self.ens.pack_terminal(self.send.data_ptr())
         if self.hdl is not None:
             self.hdl.barrier()
         else:
@@ -212,7 +221,8 @@ class FusedGather(PeerGather):
         raise RuntimeError('FusedGather has no separate gather step: begin(), run the ensemble, finish()')
 
     def close(self):
-        self.ens.set_terminal_sink([])
+        if self.in_kernel:
+            self.ens.set_terminal_sink([])
 
 
 def merge_records(recs, N, world, interleaved=False):

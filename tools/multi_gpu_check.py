@@ -23,10 +23,14 @@ torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 ok = True
 for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False),
-                             ('c4', wl.c4_vanderpol(N=50_001, tol=1e-8, t_bound=5.0), True)):
+                             ('c4', wl.c4_vanderpol(N=50_001, tol=1e-8, t_bound=5.0), True),
+                             ('c5', wl.c5_heat(N=world * 9 + 3, n=300, t_bound=1.0), False)):
     arrays, idx = nd.shard({'y0': w.y0, 'params': w.params}, rank, world, interleaved)
     f = ni.BuiltinRHS(w.rhs)
-    if w.advanced:
+    if name == 'c5':  # CTA-per-trajectory layout (the fused form packs after the run: no in-kernel sink there)
+        mk = lambda y0, par: ni.RK45(ni.rhs.heat1d(par[:, 0]), w.t0, y0, w.t_bound, rtol=w.rtol, atol=w.atol)
+        ens = mk(arrays['y0'], arrays['params'])
+    elif w.advanced:
         ens = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, arrays['y0'], arrays['params'], w.t_bound, rtol=w.rtol, atol=w.atol)
     else:
         ens = ni.RK23(f(*arrays['params'].T), w.t0, arrays['y0'], w.t_bound, rtol=w.rtol, atol=w.atol)
@@ -36,7 +40,9 @@ for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False)
     same_p = all(np.array_equal(full[k], full_p[k]) for k in full)
     # the gather fused into the integration: a fresh ensemble whose run kernel stores the terminal records to every
     # GPU's receive buffer while it integrates (FusedGather); what follows the run is a barrier
-    if w.advanced:
+    if name == 'c5':
+        ens2 = mk(arrays['y0'], arrays['params'])
+    elif w.advanced:
         ens2 = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, arrays['y0'], arrays['params'], w.t_bound, rtol=w.rtol, atol=w.atol)
     else:
         ens2 = ni.RK23(f(*arrays['params'].T), w.t0, arrays['y0'], w.t_bound, rtol=w.rtol, atol=w.atol)
@@ -51,7 +57,9 @@ for name, w, interleaved in (('c3', wl.c3_lorenz(N=200_003, t_bound=1.0), False)
     same_p = same_p and all(np.array_equal(full[k], full_f[k]) for k in full)
     fused_impl = fg.impl
     if rank == 0:
-        if w.advanced:
+        if name == 'c5':
+            ref = mk(w.y0, w.params)
+        elif w.advanced:
             ref = ni.Advanced(f.P, f.Q, ni.RK45)(f, w.t0, w.y0, w.params, w.t_bound, rtol=w.rtol, atol=w.atol)
         else:
             ref = ni.RK23(f(*w.params.T), w.t0, w.y0, w.t_bound, rtol=w.rtol, atol=w.atol)
