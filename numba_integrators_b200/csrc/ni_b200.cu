@@ -1668,6 +1668,26 @@ NI_API int ni_ensemble_get_terminal(ni_ensemble *e, void *host_out) {
   ni_ensemble_terminal_bytes(e, &rb);
   const size_t bytes = (size_t)e->N * (size_t)rb;
   CU(cudaSetDevice(e->device));
+  if (e->mod.kind == NI_KIND_LARGE) {
+    // A CTA-per-trajectory run kernel fills every SM completely (255 registers x 256 threads), and when a second
+    // ensemble's run is already queued on another stream (double buffering) its CTAs move in as this ensemble's drain:
+    // a pack KERNEL would wait behind that whole run, and with it the download and the host (measured on C5: end to end
+    // 90 instead of 79 ms per step; a high-priority stream does not help, the SMs are simply taken).  The state of these
+    // ensembles is trajectory-major already, so the copy engine assembles the records itself: one strided
+    // device-to-host copy per field, straight into the caller's record array -- no kernel on the path.
+    const size_t n = (size_t)e->mod.n, Q = (size_t)e->mod.Q, N = (size_t)e->N, pitch = (size_t)rb;
+    char *out = (char *)host_out;
+    const NiArgs &a = e->a;
+    CU(cudaMemcpy2DAsync(out, pitch, a.t, 8, 8, N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpy2DAsync(out + 8, pitch, a.y, 8 * n, 8 * n, N, cudaMemcpyDeviceToHost, e->stream));
+    if (Q) CU(cudaMemcpy2DAsync(out + 8 * (1 + n), pitch, a.aux, 8 * Q, 8 * Q, N, cudaMemcpyDeviceToHost, e->stream));
+    const size_t k0 = 8 * (1 + n + Q);
+    CU(cudaMemcpy2DAsync(out + k0, pitch, a.n_acc, 4, 4, N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpy2DAsync(out + k0 + 4, pitch, a.n_rej, 4, 4, N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpy2DAsync(out + k0 + 8, pitch, a.status, 4, 4, N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return NI_OK;
+  }
   if (int rc = need_scratch(e, bytes)) return rc;
   if (int rc = ni_ensemble_pack_terminal(e, e->scratch)) return rc;
   CU(cudaMemcpyAsync(host_out, e->scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
