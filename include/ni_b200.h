@@ -238,6 +238,12 @@ int ni_ensemble_stiffness(ni_ensemble *e, int iterations, double *rho_host);
  * expensive trajectories first (longest-processing-time-first, e.g. by the step counts of the previous run or leg of the
  * same ensemble, or by a known cost parameter such as mu of a Van der Pol sweep) leaves the cheap ones for the tail. */
 int ni_ensemble_set_order(ni_ensemble *e, const uint32_t *order_host);
+/* The same with the cost taken from the ensemble itself, entirely on the device: trajectories in decreasing order of the
+ * attempts (n_accepted + n_rejected) they have taken so far -- the previous run, or the previous leg of an integration in
+ * legs -- by a counting sort into 2048 buckets (about a millisecond for 10 M trajectories; the order inside a bucket is
+ * unspecified).  ni_ensemble_get_order copies the current order (the identity if none is set) to the host. */
+int ni_ensemble_order_by_attempts(ni_ensemble *e);
+int ni_ensemble_get_order(ni_ensemble *e, uint32_t *order_host);
 /* Guard mode (memory-safety evidence where compute-sanitizer is not available): an ensemble created while the
  * environment variable NI_B200_GUARD=1 is set keeps every device buffer between two 64 KiB guard zones filled with 0xA5.
  * *n_buffers = guarded buffers (0 when the mode is off), *bad_bytes = guard bytes that no longer hold the fill value,

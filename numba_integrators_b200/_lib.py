@@ -69,6 +69,8 @@ SIGNATURES = {
     'ni_ensemble_stiffness': (C.c_int, [_vp, C.c_int, _vp]),
     'ni_ensemble_guard_check': (C.c_int, [_vp, _i64p, _i64p]),
     'ni_ensemble_set_order': (C.c_int, [_vp, _vp]),
+    'ni_ensemble_order_by_attempts': (C.c_int, [_vp]),
+    'ni_ensemble_get_order': (C.c_int, [_vp, _vp]),
     'ni_ensemble_set_terminal_sink': (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int64]),
     'ni_ensemble_record_enable': (C.c_int, [_vp, C.c_int64]),
     'ni_ensemble_record_count': (C.c_int, [_vp, _i64p]),

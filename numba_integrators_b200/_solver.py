@@ -477,12 +477,20 @@ class Ensemble:
     def order_by_cost(self, cost=None):
         """Longest-processing-time-first launch order: trajectories sorted by decreasing `cost` (default: the attempts
         n_accepted + n_rejected they took so far -- the previous run or leg of the same ensemble, the natural predictor
-        for repeated sweeps and for integration in legs).  Returns the order that was set."""
-        if cost is None:
-            cost = np.atleast_1d(self.n_accepted).astype(np.int64) + np.atleast_1d(self.n_rejected)
+        for repeated sweeps and for integration in legs; sorted on the device, nothing crosses PCIe).  Returns the order when
+        it was computed here from `cost`, None for the device sort (`get_order()` fetches it)."""
+        if cost is None:  # on the device: counting sort by the attempts so far (~1 ms for 10 M trajectories)
+            check(self._L.ni_ensemble_order_by_attempts(self._h))
+            return None
         order = np.argsort(-np.asarray(cost), kind='stable').astype(np.uint32)
         self.set_order(order)
         return order
+
+    def get_order(self):
+        """The launch order in use (the identity if none was set)."""
+        o = np.empty(self.N, dtype=np.uint32)
+        check(self._L.ni_ensemble_get_order(self._h, o.ctypes.data))
+        return o
 
     def guard_check(self):
         """(guarded buffers, overwritten guard bytes) of an ensemble created with NI_B200_GUARD=1 in the environment:

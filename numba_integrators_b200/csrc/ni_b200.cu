@@ -1520,6 +1520,106 @@ NI_API int ni_ensemble_terminal_bytes(const ni_ensemble *e, int64_t *bytes_per_t
   return NI_OK;
 }
 
+// ---- launch order by cost on the device: counting sort of the trajectories by their attempts so far, descending.
+// Keys are bucketed (NI_ORDER_BINS buckets of 2^shift attempts): longest-first scheduling needs no finer order, and the
+// order inside a bucket may differ from run to run (atomics) -- results never depend on the launch order.
+#define NI_ORDER_BINS 2048
+__global__ void __launch_bounds__(256) ni_k_order_max(const int *n_acc, const int *n_rej, long long N, unsigned *mx) {
+  unsigned m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned k = (unsigned)(n_acc[i] + n_rej[i]);
+    m = k > m ? k : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned v = __shfl_xor_sync(0xffffffffu, m, o);
+    m = v > m ? v : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(mx, m);
+}
+__device__ __forceinline__ unsigned ni_order_bin(int acc, int rej, int shift) {
+  const unsigned k = (unsigned)(acc + rej) >> shift;
+  return NI_ORDER_BINS - 1 - (k < NI_ORDER_BINS ? k : NI_ORDER_BINS - 1);  // expensive trajectories first
+}
+__global__ void __launch_bounds__(256) ni_k_order_hist(const int *n_acc, const int *n_rej, long long N, int shift, unsigned *hist) {
+  __shared__ unsigned h[NI_ORDER_BINS];
+  for (int b = threadIdx.x; b < NI_ORDER_BINS; b += blockDim.x) h[b] = 0;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&h[ni_order_bin(n_acc[i], n_rej[i], shift)], 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b < NI_ORDER_BINS; b += blockDim.x)
+    if (h[b]) atomicAdd(&hist[b], h[b]);
+}
+__global__ void __launch_bounds__(1024) ni_k_order_scan(unsigned *hist) {  // exclusive scan in place, one block
+  __shared__ unsigned part[1024];
+  constexpr int PER = NI_ORDER_BINS / 1024;
+  unsigned v[PER], sum = 0;
+  for (int k = 0; k < PER; ++k) {
+    v[k] = hist[threadIdx.x * PER + k];
+    sum += v[k];
+  }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned add = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  unsigned base = part[threadIdx.x] - sum;
+  for (int k = 0; k < PER; ++k) {
+    hist[threadIdx.x * PER + k] = base;
+    base += v[k];
+  }
+}
+__global__ void __launch_bounds__(256) ni_k_order_scatter(const int *n_acc, const int *n_rej, long long N, int shift,
+                                                           unsigned *cursor, unsigned *order) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    order[atomicAdd(&cursor[ni_order_bin(n_acc[i], n_rej[i], shift)], 1u)] = (unsigned)i;
+}
+
+NI_API int ni_ensemble_order_by_attempts(ni_ensemble *e) {
+  if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");
+  if (!e->initialised) return fail(NI_ERR_INVALID, "ensemble is not initialised (call ni_ensemble_init)");
+  CU(cudaSetDevice(e->device));
+  const size_t N = (size_t)e->N;
+  if (!e->order_d) {
+    if (int rc = dalloc(e, &e->order_d, N)) return rc;
+    if (int rc = dalloc(e, &e->order_n_d, 1)) return rc;
+  }
+  if (int rc = need_scratch(e, (NI_ORDER_BINS + 1) * sizeof(unsigned))) return rc;
+  unsigned *hist = (unsigned *)e->scratch, *mx = hist + NI_ORDER_BINS;
+  CU(cudaMemsetAsync(hist, 0, (NI_ORDER_BINS + 1) * sizeof(unsigned), e->stream));
+  const int grid = grid_for((long long)N);
+  ni_k_order_max<<<grid, 256, 0, e->stream>>>(e->a.n_acc, e->a.n_rej, (long long)N, mx);
+  unsigned mx_h = 0;
+  CU(cudaMemcpyAsync(&mx_h, mx, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  int shift = 0;
+  while ((mx_h >> shift) >= NI_ORDER_BINS) ++shift;
+  ni_k_order_hist<<<grid, 256, 0, e->stream>>>(e->a.n_acc, e->a.n_rej, (long long)N, shift, hist);
+  ni_k_order_scan<<<1, 1024, 0, e->stream>>>(hist);
+  ni_k_order_scatter<<<grid, 256, 0, e->stream>>>(e->a.n_acc, e->a.n_rej, (long long)N, shift, hist, e->order_d);
+  CU(cudaGetLastError());
+  const unsigned long long n64 = (unsigned long long)N;
+  CU(cudaMemcpyAsync(e->order_n_d, &n64, sizeof(n64), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->n_launches += 4;
+  return NI_OK;
+}
+
+NI_API int ni_ensemble_get_order(ni_ensemble *e, uint32_t *order_host) {
+  if (!e || !order_host) return fail(NI_ERR_INVALID, "ensemble / order_host is NULL");
+  CU(cudaSetDevice(e->device));
+  if (!e->order_d) {
+    for (int64_t i = 0; i < e->N; ++i) order_host[i] = (uint32_t)i;
+    return NI_OK;
+  }
+  CU(cudaMemcpyAsync(order_host, e->order_d, (size_t)e->N * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return NI_OK;
+}
+
 // Launch order of the work queue (longest-processing-time-first scheduling against the tail of a run).
 NI_API int ni_ensemble_set_order(ni_ensemble *e, const uint32_t *order_host) {
   if (!e) return fail(NI_ERR_INVALID, "ensemble is NULL");

@@ -706,8 +706,11 @@ def test_launch_order_changes_nothing_but_the_schedule():
     b.run()
     assert np.array_equal(b.y, ref.y)
     b.set_order(None)
-    own = b.order_by_cost()    # default cost: the attempts of the ensemble's own previous run
-    assert np.array_equal(own, order)
+    assert np.array_equal(b.get_order(), np.arange(w.N))
+    assert b.order_by_cost() is None   # default cost: the attempts of the ensemble's own previous run, sorted on the device
+    own = b.get_order()
+    cost = (ref.n_accepted + ref.n_rejected)[own]
+    assert np.array_equal(np.sort(own), np.arange(w.N)) and np.all(np.diff(cost) <= 0)   # (2048 buckets of one attempt here)
     b.reset()
     b.run()
     for e in (a, b):
