@@ -551,6 +551,8 @@ def main():
         if fast is not None:
             roofline['fast'] = fast
         if ordered is not None:
+            if fp64_peak:  # (rank 0's own launch: same attempts, the ordered launch's kernel time)
+                ordered['frac'] = w.flops_per_attempt * att_rank / (ordered['run_kernel_ms_max_over_ranks'] * 1e-3) / 1e12 / fp64_peak
             line['cost_ordered'] = ordered
         if gather_ms is not None:
             # the one collective of the path, once per job after the last step: pack kernel + ONE NCCL
